@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden outputs.
+Everything here needs a B200: run with  pytest -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vjf_oracle as O
+from tests.helpers import assert_close, compare_state, load_golden, oracle_from_golden, run_phases, sub
+
+pytestmark = pytest.mark.gpu
+
+RUNS = ["c1_gauss", "pois_u", "gauss_phases", "c2_small"]
+# fp32 tolerance of the step: the CUDA path and the reference's fp32 run differ by summation order only;
+# over a run the differences are amplified by the +-1 gradient clip and the RLS conditioning, so the
+# run-level tolerance is looser than the single-step one (same figures as the oracle-vs-reference fp32 test).
+STEP_TOL = dict(rtol=5e-5, atol=5e-6)
+RUN_TOL = dict(rtol=3e-3, atol=3e-4)
+
+
+@pytest.fixture(scope="module")
+def cuda_mod():
+    from tests import gpu_helpers
+    assert torch.cuda.is_available(), "GPU tests selected without a CUDA device"
+    return gpu_helpers
+
+
+@pytest.mark.parametrize("name", RUNS)
+def test_first_step_matches_reference(cuda_mod, name):
+    g = load_golden(f"{name}_f32")
+    m = cuda_mod.CudaAsOracle(cuda_mod.model_from_golden(g))
+    n, sgd, upd, warm, _ = g["phases"][0]
+    u = g.get("u")
+    q, loss, a, b, c = m.filter(g["y"][0], None if u is None else u[0], None, eps=g["eps"][0], sgd=bool(sgd),
+                                update=bool(upd), verbose=True, warm_up=bool(warm))
+    assert_close(q.mean, g["mu"][0], what="mu[0]", **STEP_TOL)
+    assert_close(q.logvar, g["logvar"][0], what="logvar[0]", **STEP_TOL)
+    assert_close([loss, a, b, c], g["losses"][0], 5e-5, 5e-5, "losses[0]")
+    # state after one step against the oracle stepped once from the same state
+    o = oracle_from_golden(g)
+    o.filter(g["y"][0], None if u is None else u[0], None, eps=g["eps"][0], sgd=bool(sgd), update=bool(upd),
+             verbose=True, warm_up=bool(warm))
+    compare_state(cuda_mod.state_np(m.m), o.get_state(), rtol=2e-4, atol=2e-5)
+    assert m.m.status() == 0
+
+
+@pytest.mark.parametrize("name", RUNS)
+def test_run_matches_reference(cuda_mod, name):
+    g = load_golden(f"{name}_f32")
+    m = cuda_mod.CudaAsOracle(cuda_mod.model_from_golden(g))
+    mu, lv, losses = run_phases(m, g)
+    assert_close(mu, g["mu"], what="mu", **RUN_TOL)
+    assert_close(lv, g["logvar"], what="logvar", **RUN_TOL)
+    assert_close(losses, g["losses"], RUN_TOL["rtol"], 3e-3, "losses")
+    skip = ("w_pchol",)
+    got, want = cuda_mod.state_np(m.m), sub(g, "final.")
+    if name == "c1_gauss":
+        # ill-conditioned fp32 RLS (P ~ 1e4): measure against the fp64 run like tests/test_oracle_golden.py
+        skip += ("w_mean", "w_chol", "w_precision")
+        m64 = oracle_from_golden(g, dtype=np.float64)
+        run_phases(m64, g)
+        ref_err = np.abs(want["w_mean"] - m64.w_mean).max()
+        our_err = np.abs(got["w_mean"] - m64.w_mean).max()
+        assert our_err <= 2 * ref_err + 1e-4, (our_err, ref_err)
+    compare_state(got, want, skip=skip, **RUN_TOL)
+    assert m.m.status() == 0
+
+
+@pytest.mark.parametrize("name", ["c2_small", "gauss_phases"])
+def test_no_further_from_fp64_than_reference(cuda_mod, name):
+    """The CUDA fp32 path must be as close to the fp64 run of the same recipe as the reference's own
+    fp32 run is."""
+    g = load_golden(f"{name}_f32")
+    m64 = oracle_from_golden(g, dtype=np.float64)
+    mu64, lv64, _ = run_phases(m64, g)
+    m = cuda_mod.CudaAsOracle(cuda_mod.model_from_golden(g))
+    mu, lv, _ = run_phases(m, g)
+    ref = max(np.abs(g["mu"] - mu64).max(), np.abs(g["logvar"] - lv64).max())
+    ours = max(np.abs(mu - mu64).max(), np.abs(lv - lv64).max())
+    assert ours <= 4 * ref + 1e-6, (ours, ref)
+
+
+@pytest.mark.parametrize("name", ["pois_u", "c2_small", "c1_gauss"])
+def test_persistent_run_equals_stepwise(cuda_mod, name):
+    """vjf_run (T steps, one cooperative launch) == T calls of vjf_step, bit for bit."""
+    g = load_golden(f"{name}_f32")
+    a = cuda_mod.model_from_golden(g)
+    b = cuda_mod.model_from_golden(g)
+    y, eps, u = torch.as_tensor(g["y"]), torch.as_tensor(g["eps"]), g.get("u")
+    u = None if u is None else torch.as_tensor(u)
+    mu, lv, losses = a.run(y, u, None, eps=eps)
+    q = None
+    for t in range(y.shape[0]):
+        q, l0, l1, l2, l3 = b.filter(y[t], None if u is None else u[t], q, verbose=True, eps=eps[t])
+        assert torch.equal(q.mean, mu[t]) and torch.equal(q.logvar, lv[t]), t
+        assert torch.equal(torch.stack([l0, l1, l2, l3]), losses[t]), t
+    assert torch.equal(a._flat, b._flat)
+
+
+@pytest.mark.parametrize("lik,B,D,d,u,R,H", [("poisson", 300, 200, 3, 0, 50, [64]), ("gaussian", 130, 50, 4, 2, 32, [32, 16]),
+                                             ("gaussian", 1, 20, 2, 0, 100, [20]), ("poisson", 777, 64, 8, 0, 64, [128])])
+def test_seeded_steps_match_oracle(cuda_mod, lik, B, D, d, u, R, H):
+    """Seeded synthetic inputs at shapes the oracle finishes in seconds: 6 steps, every output and the
+    whole state compared with the fp64 oracle."""
+    from vjf_b200.model import VJF
+    rng = np.random.default_rng(5)
+    T = 6
+    m = VJF.make_model(D, d, u, R, H, lik, lr=1e-3, max_trials=B)
+    o = O.OracleVJF(D, d, u, R, H, lik, lr=1e-3, dtype=np.float64)
+    o.set_state(cuda_mod.state_np(m))
+    y = rng.poisson(0.7, (T, B, D)).astype(np.float32) if lik == "poisson" else rng.normal(size=(T, B, D)).astype(np.float32)
+    uu = rng.normal(size=(T, B, u)).astype(np.float32) if u else None
+    eps = rng.normal(size=(T, 2, B, d)).astype(np.float32)
+    mu, lv, losses = m.run(torch.as_tensor(y), None if uu is None else torch.as_tensor(uu), None, eps=torch.as_tensor(eps))
+    omu, olv, olosses = o.run(y.astype(np.float64), uu, eps=eps.astype(np.float64))
+    assert_close(mu.cpu().numpy(), omu, 2e-4, 2e-5, "mu")
+    assert_close(lv.cpu().numpy(), olv, 2e-4, 2e-5, "logvar")
+    assert_close(losses.cpu().numpy(), olosses, 2e-4, 2e-3, "losses")
+    compare_state(cuda_mod.state_np(m), o.get_state(), rtol=1e-3, atol=1e-4)
+    assert m.status() == 0
+
+
+def test_philox_tape_equals_in_kernel_draws(cuda_mod):
+    from vjf_b200 import _lib
+    from vjf_b200.model import VJF
+    lib = _lib.load()
+    B, d = 257, 3
+    a = VJF.make_model(30, d, 0, 10, [8], "poisson", max_trials=B, seed=1234)
+    b = VJF.make_model(30, d, 0, 10, [8], "poisson", max_trials=B, seed=1234)
+    b.load_full_state(a.full_state())
+    y = torch.poisson(torch.ones(4, B, 30))
+    eps = torch.empty(4, 2, B, d, device="cuda")
+    for t in range(4):
+        _lib.check(lib.vjf_philox_normal(1234, t, 0, B, d, C.c_void_p(eps[t].data_ptr()), None))
+    torch.cuda.synchronize()
+    mu_a, lv_a, _ = a.run(y)            # in-kernel Philox, steps 0..3
+    mu_b, lv_b, _ = b.run(y, eps=eps)   # same numbers from the tape
+    assert torch.equal(mu_a, mu_b) and torch.equal(lv_a, lv_b)
+    big = torch.empty(2, 200000, 4, device="cuda")
+    _lib.check(lib.vjf_philox_normal(7, 0, 0, 200000, 4, C.c_void_p(big.data_ptr()), None))
+    assert abs(big.mean().item()) < 5e-3 and abs(big.std().item() - 1) < 5e-3
+    assert abs((big ** 4).mean().item() - 3) < 0.1
+
+
+def test_nonfinite_term_is_zeroed_without_gradient(cuda_mod):
+    """vjf/model.py:138-145 through the in-kernel redo: same scenario as the oracle test."""
+    from vjf_b200 import _lib
+    from vjf_b200.model import VJF, Gaussian
+    m = VJF.make_model(6, 2, 0, 5, [4], "poisson", lr=1e-2, max_trials=3)
+    o = O.OracleVJF(6, 2, 0, 5, [4], "poisson", lr=1e-2, dtype=np.float64)
+    m.recognition.logvar.bias.fill_(800.0)
+    o.set_state(cuda_mod.state_np(m))
+    rng = np.random.default_rng(0)
+    y = rng.poisson(1.0, (3, 6)).astype(np.float32)
+    eps = np.zeros((2, 3, 2), np.float32)
+    q0 = Gaussian(torch.zeros(3, 2), torch.zeros(3, 2))
+    qt, loss, a, b, c = m.filter(y, None, q0, verbose=True, update=False, eps=eps)
+    oq, ol, oa, ob, oc = o.filter(y, None, O.Gaussian(np.zeros((3, 2)), np.zeros((3, 2))), eps=eps, update=False, verbose=True)
+    assert b.item() == 0 and ob == 0
+    assert_close([loss.item(), a.item(), c.item()], [ol, oa, oc], 1e-4, 1e-4, "loss terms")
+    compare_state(cuda_mod.state_np(m), o.get_state(), rtol=1e-4, atol=1e-6)
+    assert m.status() & _lib.ST_DYN_NONFINITE
+
+
+def test_split_phases_equal_fused_step(cuda_mod):
+    """phase A + local reduce + phase B (the multi-GPU split, here with one rank) == the fused step."""
+    from vjf_b200 import _lib
+    g = load_golden("pois_u_f32")
+    a = cuda_mod.model_from_golden(g)
+    b = cuda_mod.model_from_golden(g)
+    lib = _lib.load()
+    y, eps, u = torch.as_tensor(g["y"]).cuda(), torch.as_tensor(g["eps"]).cuda(), torch.as_tensor(g["u"]).cuda()
+    B, d = y.shape[1], 3
+    p = lambda t: C.c_void_p(t.data_ptr())
+    qm = ql = None
+    for t in range(5):
+        qa, la = a.filter(y[t], u[t], None if t == 0 else cuda_mod.Gaussian(qm, ql), eps=eps[t])
+        om, ol = torch.empty(B, d, device="cuda"), torch.empty(B, d, device="cuda")
+        loss = torch.empty(4, device="cuda")
+        flags = _lib.FLAG_SGD | _lib.FLAG_UPDATE | (_lib.FLAG_PRIOR_Q0 if t == 0 else 0)
+        _lib.check(lib.vjf_step_phase_a(b._h, B, B, p(y[t].contiguous()), 0, p(u[t].contiguous()), None if t == 0 else p(qm),
+                                        None if t == 0 else p(ql), p(eps[t].contiguous()), 0, t, 0, flags, p(om), p(ol), None))
+        _lib.check(lib.vjf_step_phase_b(b._h, B, flags, b.lr, p(loss), None))
+        torch.cuda.synchronize()
+        assert torch.equal(om, qa.mean) and torch.equal(ol, qa.logvar)
+        assert_close(loss[0].item(), la.item(), 1e-6, 1e-6, "loss")
+        qm, ql = qa.mean, qa.logvar
+    compare_state(cuda_mod.state_np(b), cuda_mod.state_np(a), rtol=1e-5, atol=1e-6)
+
+
+def test_run_host_equals_run(cuda_mod):
+    from vjf_b200 import _lib
+    g = load_golden("c2_small_f32")
+    a = cuda_mod.model_from_golden(g)
+    b = cuda_mod.model_from_golden(g)
+    y, eps = torch.as_tensor(g["y"]), torch.as_tensor(g["eps"])
+    T, B, D = y.shape
+    mu, lv, losses = a.run(y, None, None, eps=eps)
+    yh, eh = y.contiguous().pin_memory(), eps.contiguous().pin_memory()
+    mu_h = torch.empty(T, B, 3).pin_memory(); lv_h = torch.empty(T, B, 3).pin_memory(); ls_h = torch.empty(T, 4).pin_memory()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    flags = _lib.FLAG_SGD | _lib.FLAG_UPDATE | _lib.FLAG_PRIOR_Q0
+    _lib.check(_lib.load().vjf_run_host(b._h, T, B, p(yh), 0, None, p(eh), 0, 0, flags, b.lr, p(mu_h), p(lv_h), p(ls_h), 3))
+    assert torch.equal(mu.cpu(), mu_h) and torch.equal(lv.cpu(), lv_h) and torch.equal(losses.cpu(), ls_h)
+    assert torch.equal(a._flat, b._flat)
+    # uint8 spike counts give the same result as their float32 copy
+    c = cuda_mod.model_from_golden(g)
+    mu8, lv8, _ = c.run(y.to(torch.uint8), None, None, eps=eps)
+    assert torch.equal(mu8, mu) and torch.equal(lv8, lv)
+
+
+@pytest.mark.parametrize("tag", ["f32"])
+def test_kalman_operator(cuda_mod, tag):
+    from vjf_b200 import _lib
+    lib = _lib.load()
+    g = load_golden(f"kalman_{tag}")
+    P = 5  # the same problem replicated P times with scaled observations -> P independent problems
+    n, nb = g["x"].shape
+    m_ = g["H"].shape[0]
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(np.broadcast_to(a, (P,) + a.shape)), dtype=torch.float32).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    x, L0, A, Q, H, R, y = [dev(g[k]) for k in ("x", "L0", "A", "Q", "H", "R", "y")]
+    y = y * torch.arange(1, P + 1, device="cuda").view(P, 1, 1)
+    yhat, xhat, Lhat = torch.empty(P, m_, nb, device="cuda"), torch.empty(P, n, nb, device="cuda"), torch.empty(P, n, n, device="cuda")
+    info = torch.zeros(P, dtype=torch.int32, device="cuda")
+    _lib.check(lib.vjf_kalman_predict_batched(P, n, m_, nb, p(x), p(L0), p(A), p(Q), p(H), p(yhat), p(xhat), p(Lhat), p(info), None))
+    tol = dict(rtol=2e-4, atol=2e-5)
+    for i in range(P):
+        assert_close(yhat[i].cpu().numpy(), g["yhat"], what="yhat", **tol)
+        assert_close(xhat[i].cpu().numpy(), g["xhat"], what="xhat", **tol)
+        assert_close(Lhat[i].cpu().numpy(), g["Lhat"], what="Lhat", **tol)
+    xo, Lo = torch.empty(P, n, nb, device="cuda"), torch.empty(P, n, n, device="cuda")
+    for fn, okern in ((lib.vjf_kalman_update_batched, O.kalman_update), (lib.vjf_kalman_joseph_update_batched, O.kalman_joseph_update)):
+        _lib.check(fn(P, n, m_, nb, p(y), p(yhat), p(xhat), p(Lhat), p(H), p(R), p(xo), p(Lo), p(info), None))
+        assert int(info.abs().sum().item()) == 0
+        for i in range(P):
+            ox, oL = okern(g["y"].astype(np.float64) * (i + 1), g["yhat"].astype(np.float64), g["xhat"].astype(np.float64),
+                           g["Lhat"].astype(np.float64), g["H"].astype(np.float64), g["R"].astype(np.float64))
+            assert_close(xo[i].cpu().numpy(), ox, what=f"x[{i}]", **tol)
+            assert_close(Lo[i].cpu().numpy(), oL, what=f"L[{i}]", **tol)
+    # golden vectors of the reference itself (problem 0 has the unscaled y)
+    _lib.check(lib.vjf_kalman_update_batched(P, n, m_, nb, p(y), p(yhat), p(xhat), p(Lhat), p(H), p(R), p(xo), p(Lo), p(info), None))
+    assert_close(xo[0].cpu().numpy(), g["x_upd"], what="x_upd", **tol)
+    assert_close(Lo[0].cpu().numpy(), g["L_upd"], what="L_upd", **tol)
+    _lib.check(lib.vjf_kalman_joseph_update_batched(P, n, m_, nb, p(y), p(yhat), p(xhat), p(Lhat), p(H), p(R), p(xo), p(Lo), p(info), None))
+    assert_close(xo[0].cpu().numpy(), g["x_jos"], what="x_jos", **tol)
+    assert_close(Lo[0].cpu().numpy(), g["L_jos"], what="L_jos", **tol)
+    a = dev(g["sym_in"]); out = torch.empty_like(a)
+    _lib.check(lib.vjf_symmetrize_batched(P, n, p(a), p(out), None))
+    assert np.array_equal(out[2].cpu().numpy(), g["sym_out"])
+    a = dev(g["pos_in"])
+    _lib.check(lib.vjf_positivize_batched(P, n, p(a), 1e-3, p(out), None))
+    assert_close(out[3].cpu().numpy(), g["pos_out"], 1e-3, 1e-4, "positivize")
+
+
+def test_initialize_and_forecast_match_oracle(cuda_mod):
+    from vjf_b200.model import VJF
+    rng = np.random.default_rng(3)
+    D, d, u, R = 15, 3, 1, 12
+    m = VJF.make_model(D, d, u, R, [7], "gaussian", max_trials=64)
+    o = O.OracleVJF(D, d, u, R, [7], "gaussian", dtype=np.float64)
+    o.set_state(cuda_mod.state_np(m))
+    N = 333
+    xs = rng.normal(size=(N, d)); xt = xs + 0.1 * np.sin(xs) + 0.05 * rng.normal(size=(N, d)); ut = rng.normal(size=(N, u))
+    r_guess = float(np.sqrt((np.concatenate([xs, ut], -1) ** 2).sum(1)).max())
+    cen = rng.uniform(-r_guess, r_guess, size=(R, d + u))
+    r = m.initialize_transition(torch.as_tensor(xt), torch.as_tensor(xs), torch.as_tensor(ut), centroid=torch.as_tensor(cen))
+    st, ro = o.initialize_transition(xt, xs, ut, centroid=cen)
+    assert abs(r - ro) < 1e-4 * ro and st == 0
+    compare_state(cuda_mod.state_np(m), o.get_state(), rtol=2e-3, atol=2e-4)
+    # forecast with injected draws
+    n_step, B = 9, 5
+    w_eps = rng.normal(size=(n_step, R, d)); x_eps = rng.normal(size=(n_step, B, d)); uf = rng.normal(size=(n_step, B, u))
+    x0 = rng.normal(size=(B, d))
+    x, yh = m.forecast(x0, uf, n_step, noise=True, w_eps=w_eps, x_eps=x_eps)
+    ox, oy = o.forecast(x0, uf, n_step, noise=True, w_eps=w_eps, x_eps=x_eps)
+    assert_close(x.cpu().numpy(), ox, 2e-3, 2e-4, "forecast x")
+    assert_close(yh.cpu().numpy(), oy, 2e-3, 2e-4, "forecast y")

@@ -1,0 +1,173 @@
+// Shared device/host definitions for the vjf_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/vjf_b200.h"
+
+#define VJF_NT 512               // threads per CTA of the step kernels
+#define VJF_NWARP (VJF_NT / 32)
+#define VJF_TB_MAX 32            // trials per tile (rows of the per-CTA tile)
+#define VJF_NSCAL 8              // scalar sums carried in the partial vector
+
+// scalar slots
+#define SC_RECON 0   // sum_b sum_j recon terms (without the 0.5*lambda*D constant)
+#define SC_DYN 1     // sum_b sum_i dyn terms (without 0.5*gamma*d)
+#define SC_ENT 2     // sum_b sum_i 0.5*l_t
+#define SC_SSE 3     // sum (y-eta)^2            (Gaussian likelihood.update)
+#define SC_SDX 4     // sum dx^2                 (state-noise residual algebra)
+#define SC_BADMSE 5  // count of non-finite squared errors (functional.py:60 assert)
+
+struct Lay {  // int copies of vjf_layout (state buffers are < 2^31 floats)
+  int lik_logvar, dec_w, dec_b, mlp_w[VJF_MAX_LAYERS], mlp_b[VJF_MAX_LAYERS], head_m_w, head_v_w, head_v_b, n_train;
+  int prior_mean, prior_logvar, tr_logvar, centroid, logwidth, w_mean, w_chol, w_precision, w_pchol, lik_n, tr_n, total;
+};
+
+struct StepParams {
+  // ---- dimensions ----
+  int B, Bglobal, D, d, u, R, L, H[VJF_MAX_LAYERS];
+  int K1, K1p, E, du, Dp, Rp, Hp[VJF_MAX_LAYERS], Hpmax;
+  int lik;
+  Lay lay;
+  // ---- partial-sum vector layout: [0,G) grads | A (R*R) | b (R*d) | scalars ----
+  int G, pa, pb, ps, PS;
+  // ---- tiling ----
+  int TB, ntiles, nslots;
+  // ---- shared-memory plan (float offsets) ----
+  int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
+      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_total;
+  int U_in_smem;
+  int ldm;  // row stride of the factorisation workspace in phase B2
+  // ---- pointers ----
+  float* state;
+  float* partials;      // [nslots][PS]
+  float* reduced;       // [PS]
+  unsigned* barrier;    // grid barrier counter
+  unsigned* status;     // status word
+  unsigned* ctrl;       // [0] term masks of the current step (persistent redo)
+  const void* y;
+  int y_dtype;
+  const float* u_in;
+  const float* q0m;
+  const float* q0l;
+  const float* eps;
+  float* mu;
+  float* logvar;
+  float* losses;
+  unsigned long long seed, step0, trial_offset;
+  unsigned flags;
+  float lr;
+  int T;
+  int red_begin;   // first element of the partial vector the reduction touches
+  int init_mode;   // phase B2 runs as RBFDS.initialize (vjf/model.py:379-388) instead of a filter step
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for the persistent (cooperatively launched) kernel.  `target` is a per-thread
+// running count of expected arrivals; the counter is zeroed by the host before each launch.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    red_release_add_u32(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();  // gpu-scope fence: also drops stale L1 lines before the CTA reads peers' data
+  }
+  __syncthreads();
+}
+
+// Philox4x32-10 (Salmon et al. 2011) -> 4 x N(0,1) by Box-Muller.  Keyed by (seed, step); counter =
+// (trial index, which draw, 4-block of the state dimension).  Used identically by the step kernels and
+// by vjf_philox_normal() so that tape mode and in-kernel mode produce the same numbers.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += W0; k1 += W1;
+  }
+}
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned long long step, unsigned long long trial,
+                                               uint32_t which, uint32_t blk, float out[4]) {
+  uint32_t c[4] = {(uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)step, (which << 16) | blk};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32);
+  philox4x32_10(c, k0, k1);
+  const float TWO_PI = 6.283185307179586f;
+  // (0,1] uniforms so that log() is finite
+  float u0 = ((float)(c[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  float u1 = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
+  float u2 = ((float)(c[2] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  float u3 = (float)(c[3] >> 8) * (1.0f / 16777216.0f);
+  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincosf(TWO_PI * u1, &s0, &c0);
+  sincosf(TWO_PI * u3, &s1, &c1);
+  out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
+}
+
+// clamp that propagates NaN the way torch.clamp does (fminf/fmaxf would drop it)
+__device__ __forceinline__ float clip1(float g) { return g < -1.0f ? -1.0f : (g > 1.0f ? 1.0f : g); }
+
+// internal host API shared by the translation units
+struct vjf_handle {
+  vjf_config cfg;
+  vjf_layout lay64;
+  StepParams base;       // dims, layout, pointers to workspace; per-call fields filled by the entry points
+  float* state;
+  float* partials;
+  float* reduced;
+  unsigned* sync_words;  // [0] barrier, [1] status, [2..] ctrl
+  int device;
+  int num_sms;
+  int max_slots;
+  size_t smem_limit;
+  // staging for vjf_run_host
+  void* stage_y[2];
+  float* stage_u[2];
+  float* stage_eps[2];
+  float* stage_mu;
+  float* stage_lv;
+  float* stage_loss;
+  size_t stage_y_sz[2], stage_u_sz[2], stage_eps_sz[2], stage_mu_sz, stage_lv_sz, stage_loss_sz;
+  cudaStream_t copy_stream, compute_stream;
+  cudaEvent_t ev_copied[2], ev_done[2];
+};
+
+void vjf_set_error(const char* fmt, ...);
+extern long long g_vjf_launches;
+#define VJF_CUDA_OK(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      vjf_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                                  \
+    }                                                                                             \
+  } while (0)

@@ -1,0 +1,484 @@
+// Kernels + C ABI of the VJF filter/learning step.  See include/vjf_b200.h for the contract.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+#include "step_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error handling / accounting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+long long g_vjf_launches = 0;
+
+void vjf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* vjf_last_error(void) { return g_err; }
+extern "C" int vjf_version(void) { return 100; }
+extern "C" int64_t vjf_launch_count(void) { return g_vjf_launches; }
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned base_masks(const StepParams& p) {
+  return 1u | ((p.flags & VJF_FLAG_WARMUP) ? 0u : 2u) | 4u;
+}
+
+// The whole time loop in one cooperative launch: T x {phase A | barrier | B1 | barrier | B2 | barrier}.
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  unsigned target = 0;
+  for (int t = 0; t < p.T; ++t) {
+    unsigned masks = base_masks(p), fin;
+    for (int attempt = 0;; ++attempt) {
+      phase_a(p, sm, t, masks);
+      grid_barrier(p.barrier, target);
+      fin = term_finite_mask(p, p.partials, gridDim.x, sm);
+      // vjf/model.py:138-145: a non-finite term becomes the constant 0 => it must not contribute a
+      // gradient either.  Rare; redo the trial-parallel phase with that term switched off.
+      const unsigned nm = masks & (fin | ~7u);
+      if (attempt == 0 && nm != masks && (p.flags & VJF_FLAG_SGD)) {
+        masks = nm;
+        grid_barrier(p.barrier, target);
+        continue;
+      }
+      break;
+    }
+    phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x);
+    grid_barrier(p.barrier, target);
+    if (blockIdx.x == 0) phase_b2(p, sm, t, fin);
+    grid_barrier(p.barrier, target);
+  }
+}
+
+// ---- split path (trials sharded over GPUs): phase A | local reduce | <all-reduce by the caller> | phase B ----
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_phase_a_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  phase_a(p, sm, 0, base_masks(p));
+}
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_reduce_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  phase_b1(p, sm, p.partials, p.nslots, false, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_phase_b_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  unsigned fin = 0;
+  for (int i = 0; i < 3; ++i)
+    if (isfinite(p.reduced[p.ps + i])) fin |= 1u << i;
+  const unsigned need = base_masks(p);
+  // without the in-kernel redo a non-finite term cannot be separated from the gradient: skip the SGD
+  // step (the reference's "RuntimeError -> skip" branch, vjf/model.py:212-214) and flag it
+  if ((fin & need) == need) sgd_from_reduced(p, blockIdx.x, gridDim.x);
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    phase_b2(p, sm, 0, fin);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+static inline int64_t up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int vjf_get_layout(const vjf_config* c, vjf_layout* o) {
+  if (!c || !o) { vjf_set_error("null argument"); return -1; }
+  if (c->ydim < 1 || c->xdim < 1 || c->xdim > VJF_MAX_XDIM || c->udim < 0 || c->n_rbf < 1 || c->n_layers < 1 ||
+      c->n_layers > VJF_MAX_LAYERS) {
+    vjf_set_error("unsupported configuration: need 1<=xdim<=%d, 1<=len(hidden_sizes)<=%d, ydim>=1, n_rbf>=1",
+                  VJF_MAX_XDIM, VJF_MAX_LAYERS);
+    return -1;
+  }
+  for (int l = 0; l < c->n_layers; ++l)
+    if (c->hidden[l] < 1) { vjf_set_error("hidden size must be positive"); return -1; }
+  const int64_t D = c->ydim, d = c->xdim, u = c->udim, R = c->n_rbf;
+  memset(o, 0, sizeof(*o));
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t at = off; off = up(off + n, 32); return at; };
+  o->lik_logvar = take(1);
+  o->dec_w = take(d * D);
+  o->dec_b = take(D);
+  int64_t in = D + u + 2 * d;
+  for (int l = 0; l < c->n_layers; ++l) {
+    o->mlp_w[l] = take(in * c->hidden[l]);
+    o->mlp_b[l] = take(c->hidden[l]);
+    in = c->hidden[l];
+  }
+  o->head_m_w = take(in * d);
+  o->head_v_w = take(in * d);
+  o->head_v_b = take(d);
+  o->n_train = off;
+  o->prior_mean = take(d);
+  o->prior_logvar = take(d);
+  o->tr_logvar = take(1);
+  o->centroid = take(R * (d + u));
+  o->logwidth = take(R);
+  o->w_mean = take(R * d);
+  o->w_chol = take(R * R);
+  o->w_precision = take(R * R);
+  o->w_pchol = take(R * R);
+  o->lik_n = take(1);
+  o->tr_n = take(1);
+  o->total = off;
+  if (o->total >= (int64_t)1 << 31) { vjf_set_error("state buffer too large"); return -1; }
+  return 0;
+}
+
+static void lay_to_int(const vjf_layout& a, Lay& b) {
+  b.lik_logvar = (int)a.lik_logvar; b.dec_w = (int)a.dec_w; b.dec_b = (int)a.dec_b;
+  for (int l = 0; l < VJF_MAX_LAYERS; ++l) { b.mlp_w[l] = (int)a.mlp_w[l]; b.mlp_b[l] = (int)a.mlp_b[l]; }
+  b.head_m_w = (int)a.head_m_w; b.head_v_w = (int)a.head_v_w; b.head_v_b = (int)a.head_v_b; b.n_train = (int)a.n_train;
+  b.prior_mean = (int)a.prior_mean; b.prior_logvar = (int)a.prior_logvar; b.tr_logvar = (int)a.tr_logvar;
+  b.centroid = (int)a.centroid; b.logwidth = (int)a.logwidth; b.w_mean = (int)a.w_mean; b.w_chol = (int)a.w_chol;
+  b.w_precision = (int)a.w_precision; b.w_pchol = (int)a.w_pchol; b.lik_n = (int)a.lik_n; b.tr_n = (int)a.tr_n;
+  b.total = (int)a.total;
+}
+
+// shared-memory plan for a tile of `tb` rows; returns the number of floats (phase A vs phase B2 maximum)
+static size_t plan_smem(StepParams& p, int tb, bool u_in_smem) {
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t at = off; off = (off + n + 3) & ~(size_t)3; return (int)at; };
+  p.s_in = take((size_t)tb * p.K1p);
+  p.s_g = take((size_t)tb * p.Dp);
+  p.s_phi = take((size_t)tb * p.Rp);
+  for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)tb * p.Hp[l]);
+  p.s_gpa = take((size_t)tb * p.Hpmax);
+  p.s_gpb = take((size_t)tb * p.Hpmax);
+  p.s_eps = take((size_t)tb * 2 * p.d);
+  p.s_xu = take((size_t)tb * p.du);
+  p.s_xt = take((size_t)tb * p.d); p.s_mt = take((size_t)tb * p.d); p.s_lt = take((size_t)tb * p.d);
+  p.s_pm = take((size_t)tb * p.d); p.s_dx = take((size_t)tb * p.d); p.s_gxt = take((size_t)tb * p.d);
+  p.s_gmt = take((size_t)tb * p.d); p.s_glt = take((size_t)tb * p.d); p.s_plv = take((size_t)tb);
+  p.U_in_smem = u_in_smem ? 1 : 0;
+  p.s_U = take(u_in_smem ? (size_t)p.R * p.R : 0);
+  p.s_W = take((size_t)p.R * p.d);
+  p.s_c = take((size_t)p.R * p.du);
+  p.s_iw = take((size_t)p.R);
+  p.s_red = take((size_t)VJF_NWARP * VJF_NSCAL + 64);
+  const size_t a = off;
+  // phase B2: [(2R+d)][ldm] + pivots + double scratch ; phase B1: 512 floats
+  const size_t b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
+  p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
+  return (size_t)p.s_total;
+}
+
+static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots) {
+  if (B < 1 || B > h->cfg.max_trials) { vjf_set_error("trials B=%d outside [1, max_trials=%d]", B, h->cfg.max_trials); return -1; }
+  int tb = (int)up((B + max_slots - 1) / max_slots, 4);
+  tb = std::min(std::max(tb, 4), VJF_TB_MAX);
+  const size_t limit = h->smem_limit;
+  bool u_smem = (size_t)p.R * p.R * 4 <= 96 * 1024;
+  for (;;) {
+    if (plan_smem(p, tb, u_smem) * 4 <= limit) break;
+    if (tb > 4) { tb -= 4; continue; }
+    if (u_smem) { u_smem = false; tb = std::min(std::max((int)up((B + max_slots - 1) / max_slots, 4), 4), VJF_TB_MAX); continue; }
+    vjf_set_error("configuration does not fit in %zu bytes of shared memory (ydim=%d n_rbf=%d)", limit, p.D, p.R);
+    return -1;
+  }
+  const size_t b2 = ((size_t)(2 * p.R + p.d) * p.ldm + p.R + 64) * 4;
+  if (b2 > limit) { vjf_set_error("n_rbf=%d too large for the single-CTA RLS factorisation of this build", p.R); return -1; }
+  p.B = B;
+  p.TB = tb;
+  p.ntiles = (B + tb - 1) / tb;
+  p.nslots = std::min(p.ntiles, max_slots);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------
+extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out) {
+  if (!cfg || !state || !out) { vjf_set_error("null argument"); return -1; }
+  vjf_layout lay;
+  if (vjf_get_layout(cfg, &lay)) return -1;
+  if (cfg->max_trials < 1) { vjf_set_error("max_trials must be >= 1"); return -1; }
+  if (cfg->likelihood != VJF_LIK_POISSON && cfg->likelihood != VJF_LIK_GAUSSIAN) { vjf_set_error("unknown likelihood id"); return -1; }
+  vjf_handle* h = (vjf_handle*)calloc(1, sizeof(vjf_handle));
+  h->cfg = *cfg;
+  h->lay64 = lay;
+  h->state = state;
+  VJF_CUDA_OK(cudaGetDevice(&h->device));
+  cudaDeviceProp prop;
+  VJF_CUDA_OK(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) {
+    vjf_set_error("vjf_b200 is built for sm_100a (B200); found compute capability %d.%d -- there is no fallback path", prop.major, prop.minor);
+    free(h);
+    return -3;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  h->smem_limit = prop.sharedMemPerBlockOptin;
+  VJF_CUDA_OK(cudaFuncSetAttribute(vjf_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
+  VJF_CUDA_OK(cudaFuncSetAttribute(vjf_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
+  VJF_CUDA_OK(cudaFuncSetAttribute(vjf_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
+  h->max_slots = h->num_sms;  // one persistent CTA per SM
+
+  StepParams& p = h->base;
+  memset(&p, 0, sizeof(p));
+  p.D = cfg->ydim; p.d = cfg->xdim; p.u = cfg->udim; p.R = cfg->n_rbf; p.L = cfg->n_layers;
+  p.K1 = p.D + p.u + 2 * p.d; p.K1p = (int)up(p.K1, 4); p.E = p.u + 2 * p.d; p.du = p.d + p.u;
+  p.Dp = (int)up(p.D, 4); p.Rp = (int)up(p.R, 4);
+  p.Hpmax = 4;
+  for (int l = 0; l < p.L; ++l) { p.H[l] = cfg->hidden[l]; p.Hp[l] = (int)up(p.H[l], 4); p.Hpmax = std::max(p.Hpmax, p.Hp[l]); }
+  p.lik = cfg->likelihood;
+  lay_to_int(lay, p.lay);
+  p.G = p.lay.n_train;
+  p.pa = p.G;
+  p.pb = (int)up(p.pa + (int64_t)p.R * p.R, 4);
+  p.ps = (int)up(p.pb + (int64_t)p.R * p.d, 4);
+  p.PS = p.ps + VJF_NSCAL;
+  p.ldm = (p.R + 1) | 1;
+  p.state = state;
+
+  const size_t part_bytes = (size_t)h->max_slots * p.PS * sizeof(float);
+  VJF_CUDA_OK(cudaMalloc(&h->partials, part_bytes));
+  VJF_CUDA_OK(cudaMemset(h->partials, 0, part_bytes));
+  VJF_CUDA_OK(cudaMalloc(&h->reduced, (size_t)p.PS * sizeof(float)));
+  VJF_CUDA_OK(cudaMemset(h->reduced, 0, (size_t)p.PS * sizeof(float)));
+  VJF_CUDA_OK(cudaMalloc(&h->sync_words, 64 * sizeof(unsigned)));
+  VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
+  p.partials = h->partials; p.reduced = h->reduced;
+  p.barrier = h->sync_words; p.status = h->sync_words + 16; p.ctrl = h->sync_words + 32;
+  *out = h;
+  return 0;
+}
+
+extern "C" int vjf_destroy(vjf_handle* h) {
+  if (!h) return 0;
+  cudaFree(h->partials); cudaFree(h->reduced); cudaFree(h->sync_words);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->stage_y[i]); cudaFree(h->stage_u[i]); cudaFree(h->stage_eps[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+  free(h);
+  return 0;
+}
+
+__global__ void vjf_init_state_kernel(float* st, Lay lay, int R, int d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R * R) {
+    const float v = (i / R == i % R) ? 1.0f : 0.0f;  // vjf/module.py:52-54
+    st[lay.w_chol + i] = v; st[lay.w_precision + i] = v; st[lay.w_pchol + i] = v;
+  }
+  if (i < R * d) st[lay.w_mean + i] = 0.f;            // module.py:46
+  if (i < R) st[lay.logwidth + i] = 0.f;              // module.py:21
+  if (i < d) { st[lay.prior_mean + i] = 0.f; st[lay.prior_logvar + i] = 0.f; }  // model.py:66-67
+  if (i == 0) {
+    st[lay.lik_logvar] = logf(0.1f);                  // likelihood.py:16
+    st[lay.tr_logvar] = 0.f;                          // model.py:331
+    st[lay.lik_n] = 0.f; st[lay.tr_n] = 0.f;
+  }
+}
+
+extern "C" int vjf_init_state(vjf_handle* h, void* stream) {
+  if (!h) { vjf_set_error("null handle"); return -1; }
+  const int R = h->base.R, n = R * R;
+  vjf_init_state_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->state, h->base.lay, R, h->base.d);
+  ++g_vjf_launches;
+  VJF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// step / run
+// ------------------------------------------------------------------------------------------
+static int launch_persistent(vjf_handle* h, StepParams& p, cudaStream_t s) {
+  VJF_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
+  void* args[] = {(void*)&p};
+  VJF_CUDA_OK(cudaLaunchCooperativeKernel((void*)vjf_persistent_kernel, dim3(p.nslots), dim3(VJF_NT), args,
+                                          (size_t)p.s_total * sizeof(float), s));
+  ++g_vjf_launches;
+  return 0;
+}
+
+static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const float* qm, const float* ql, uint32_t flags,
+                      const float* mu, const float* lv) {
+  if (!h) { vjf_set_error("null handle"); return -1; }
+  if (!y || !mu || !lv) { vjf_set_error("null y / output pointer"); return -1; }
+  if (h->cfg.udim > 0 && !u) { vjf_set_error("udim=%d but u is NULL", h->cfg.udim); return -1; }
+  if (!(flags & VJF_FLAG_PRIOR_Q0) && (!qm || !ql)) { vjf_set_error("previous posterior is NULL and VJF_FLAG_PRIOR_Q0 is not set"); return -1; }
+  return 0;
+}
+
+extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32_t y_dtype, const float* u,
+                       const float* q0_mean, const float* q0_logvar, const float* eps, uint64_t seed, uint64_t step0,
+                       uint32_t flags, float lr, float* mu, float* logvar, float* losses, void* stream) {
+  if (check_ptrs(h, y, u, q0_mean, q0_logvar, flags, mu, logvar)) return -1;
+  if (T < 1) { vjf_set_error("T must be >= 1"); return -1; }
+  if (y_dtype != VJF_Y_F32 && y_dtype != VJF_Y_U8) { vjf_set_error("unknown y dtype"); return -1; }
+  StepParams p = h->base;
+  if (plan_tiles(h, p, B, h->max_slots)) return -1;
+  p.Bglobal = B;
+  p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
+  p.mu = mu; p.logvar = logvar; p.losses = losses;
+  p.seed = seed; p.step0 = step0; p.trial_offset = 0; p.flags = flags; p.lr = lr; p.T = T;
+  return launch_persistent(h, p, (cudaStream_t)stream);
+}
+
+extern "C" int vjf_step(vjf_handle* h, int32_t B, const float* y, const float* u, const float* q_mean, const float* q_logvar,
+                        const float* eps, uint64_t seed, uint64_t step_index, uint32_t flags, float lr, float* out_mean,
+                        float* out_logvar, float* out_loss, void* stream) {
+  return vjf_run(h, 1, B, y, VJF_Y_F32, u, q_mean, q_logvar, eps, seed, step_index, flags, lr, out_mean, out_logvar,
+                 out_loss, stream);
+}
+
+int vjf_internal_reduce(const StepParams& p, cudaStream_t s) {
+  vjf_reduce_kernel<<<(p.PS - p.red_begin + 127) / 128, VJF_NT, 2048, s>>>(p);
+  ++g_vjf_launches;
+  VJF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t vjf_reduce_size(vjf_handle* h) { return h ? h->base.PS : -1; }
+extern "C" float* vjf_reduce_buffer(vjf_handle* h) { return h ? h->reduced : nullptr; }
+
+extern "C" int vjf_step_phase_a(vjf_handle* h, int32_t B_local, int32_t B_global, const float* y, int32_t y_dtype,
+                                const float* u, const float* q_mean, const float* q_logvar, const float* eps, uint64_t seed,
+                                uint64_t step_index, uint64_t trial_offset, uint32_t flags, float* out_mean, float* out_logvar,
+                                void* stream) {
+  if (check_ptrs(h, y, u, q_mean, q_logvar, flags, out_mean, out_logvar)) return -1;
+  StepParams p = h->base;
+  if (plan_tiles(h, p, B_local, h->max_slots)) return -1;
+  p.Bglobal = B_global;
+  p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q_mean; p.q0l = q_logvar; p.eps = eps;
+  p.mu = out_mean; p.logvar = out_logvar; p.losses = nullptr;
+  p.seed = seed; p.step0 = step_index; p.trial_offset = trial_offset; p.flags = flags; p.lr = 0.f; p.T = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  vjf_phase_a_kernel<<<p.nslots, VJF_NT, (size_t)p.s_total * sizeof(float), s>>>(p);
+  ++g_vjf_launches;
+  VJF_CUDA_OK(cudaGetLastError());
+  if (vjf_internal_reduce(p, s)) return -2;
+  return 0;
+}
+
+extern "C" int vjf_step_phase_b(vjf_handle* h, int32_t B_global, uint32_t flags, float lr, float* out_loss, void* stream) {
+  if (!h) { vjf_set_error("null handle"); return -1; }
+  StepParams p = h->base;
+  if (plan_tiles(h, p, 1, h->max_slots)) return -1;  // only the B2 workspace matters here
+  p.Bglobal = B_global; p.B = B_global;
+  p.flags = flags; p.lr = lr; p.T = 1; p.losses = out_loss;
+  const int grid = std::max(1, std::min(h->num_sms, (p.lay.n_train + VJF_NT - 1) / VJF_NT));
+  vjf_phase_b_kernel<<<grid, VJF_NT, (size_t)p.s_total * sizeof(float), (cudaStream_t)stream>>>(p);
+  ++g_vjf_launches;
+  VJF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear) {
+  if (!h || !out) { vjf_set_error("null argument"); return -1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  VJF_CUDA_OK(cudaMemcpyAsync(out, h->base.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (clear) VJF_CUDA_OK(cudaMemsetAsync(h->base.status, 0, sizeof(uint32_t), s));
+  VJF_CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox tape (lets a caller reproduce, outside the kernel, the very numbers it draws)
+// ------------------------------------------------------------------------------------------
+__global__ void vjf_philox_kernel(unsigned long long seed, unsigned long long step, unsigned long long off, int B, int d,
+                                  float* out) {
+  const int nblk = (d + 3) >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * nblk) return;
+  const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
+  float z[4];
+  philox_normal4(seed, step, off + b, which, blk, z);
+  for (int k = 0; k < 4; ++k)
+    if (blk * 4 + k < d) out[((size_t)which * B + b) * d + blk * 4 + k] = z[k];
+}
+
+extern "C" int vjf_philox_normal(uint64_t seed, uint64_t step_index, uint64_t trial_offset, int32_t B, int32_t xdim,
+                                 float* eps_out, void* stream) {
+  if (!eps_out || B < 1 || xdim < 1) { vjf_set_error("bad argument"); return -1; }
+  const int n = B * 2 * ((xdim + 3) / 4);
+  vjf_philox_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, step_index, trial_offset, B, xdim, eps_out);
+  ++g_vjf_launches;
+  VJF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// end-to-end entry with host buffers: chunked, double-buffered H2D overlapped with compute
+// ------------------------------------------------------------------------------------------
+static int ensure(void** p, size_t* have, size_t need) {
+  if (*have >= need) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  VJF_CUDA_OK(cudaMalloc(p, need));
+  *have = need;
+  return 0;
+}
+
+extern "C" int vjf_run_host(vjf_handle* h, int32_t T, int32_t B, const void* y_host, int32_t y_dtype, const float* u_host,
+                            const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu_host,
+                            float* logvar_host, float* losses_host, int32_t chunk_steps) {
+  if (!h || !y_host || !mu_host || !logvar_host) { vjf_set_error("null argument"); return -1; }
+  if (h->cfg.udim > 0 && !u_host) { vjf_set_error("udim=%d but u is NULL", h->cfg.udim); return -1; }
+  if (!(flags & VJF_FLAG_PRIOR_Q0)) { vjf_set_error("vjf_run_host starts from the prior: set VJF_FLAG_PRIOR_Q0"); return -1; }
+  if (T < 1 || chunk_steps < 1) { vjf_set_error("T and chunk_steps must be >= 1"); return -1; }
+  const int D = h->cfg.ydim, d = h->cfg.xdim, u = h->cfg.udim;
+  const size_t ysz = (y_dtype == VJF_Y_U8) ? 1 : 4;
+  const int C = std::min(chunk_steps, T);
+  if (!h->copy_stream) {
+    VJF_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    VJF_CUDA_OK(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      VJF_CUDA_OK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+      VJF_CUDA_OK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  // device staging: y/u/eps double-buffered per chunk; trajectory for the whole chunk pair
+  const size_t yb = (size_t)C * B * D * ysz, ub = (size_t)C * B * u * 4, eb = (size_t)C * 2 * B * d * 4;
+  const size_t tb = (size_t)(C + 1) * B * d * 4, lb = (size_t)C * 4 * 4;
+  for (int i = 0; i < 2; ++i) {
+    if (ensure(&h->stage_y[i], &h->stage_y_sz[i], yb)) return -2;
+    if (u && ensure((void**)&h->stage_u[i], &h->stage_u_sz[i], ub)) return -2;
+    if (eps_host && ensure((void**)&h->stage_eps[i], &h->stage_eps_sz[i], eb)) return -2;
+  }
+  // trajectory staging holds [carry | C steps] for two chunks in flight
+  if (ensure((void**)&h->stage_mu, &h->stage_mu_sz, 2 * tb)) return -2;
+  if (ensure((void**)&h->stage_lv, &h->stage_lv_sz, 2 * tb)) return -2;
+  if (ensure((void**)&h->stage_loss, &h->stage_loss_sz, 2 * lb)) return -2;
+  cudaStream_t cs = h->copy_stream, ks = h->compute_stream;
+  const int nchunks = (T + C - 1) / C;
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1, t0 = c * C, n = std::min(C, T - t0);
+    if (c >= 2) VJF_CUDA_OK(cudaStreamWaitEvent(cs, h->ev_done[buf], 0));
+    VJF_CUDA_OK(cudaMemcpyAsync(h->stage_y[buf], (const char*)y_host + (size_t)t0 * B * D * ysz, (size_t)n * B * D * ysz,
+                                cudaMemcpyHostToDevice, cs));
+    if (u) VJF_CUDA_OK(cudaMemcpyAsync(h->stage_u[buf], u_host + (size_t)t0 * B * u, (size_t)n * B * u * 4, cudaMemcpyHostToDevice, cs));
+    if (eps_host) VJF_CUDA_OK(cudaMemcpyAsync(h->stage_eps[buf], eps_host + (size_t)t0 * 2 * B * d, (size_t)n * 2 * B * d * 4, cudaMemcpyHostToDevice, cs));
+    VJF_CUDA_OK(cudaEventRecord(h->ev_copied[buf], cs));
+    VJF_CUDA_OK(cudaStreamWaitEvent(ks, h->ev_copied[buf], 0));
+    // trajectory slab of this chunk: row 0 = carry (q of the last step of the previous chunk)
+    float* mu_d = h->stage_mu + (size_t)buf * (C + 1) * B * d;
+    float* lv_d = h->stage_lv + (size_t)buf * (C + 1) * B * d;
+    float* loss_d = h->stage_loss + (size_t)buf * C * 4;
+    if (c > 0) {
+      const int pb = (c - 1) & 1, pn = std::min(C, T - (c - 1) * C);
+      VJF_CUDA_OK(cudaMemcpyAsync(mu_d, h->stage_mu + ((size_t)pb * (C + 1) + pn) * B * d, (size_t)B * d * 4, cudaMemcpyDeviceToDevice, ks));
+      VJF_CUDA_OK(cudaMemcpyAsync(lv_d, h->stage_lv + ((size_t)pb * (C + 1) + pn) * B * d, (size_t)B * d * 4, cudaMemcpyDeviceToDevice, ks));
+    }
+    const uint32_t fl = (c == 0) ? flags : (flags & ~(uint32_t)VJF_FLAG_PRIOR_Q0);
+    if (vjf_run(h, n, B, h->stage_y[buf], y_dtype, u ? h->stage_u[buf] : nullptr, mu_d, lv_d,
+                eps_host ? h->stage_eps[buf] : nullptr, seed, step0 + t0, fl, lr, mu_d + (size_t)B * d, lv_d + (size_t)B * d,
+                loss_d, ks))
+      return -2;
+    VJF_CUDA_OK(cudaMemcpyAsync(mu_host + (size_t)t0 * B * d, mu_d + (size_t)B * d, (size_t)n * B * d * 4, cudaMemcpyDeviceToHost, ks));
+    VJF_CUDA_OK(cudaMemcpyAsync(logvar_host + (size_t)t0 * B * d, lv_d + (size_t)B * d, (size_t)n * B * d * 4, cudaMemcpyDeviceToHost, ks));
+    if (losses_host) VJF_CUDA_OK(cudaMemcpyAsync(losses_host + (size_t)t0 * 4, loss_d, (size_t)n * 16, cudaMemcpyDeviceToHost, ks));
+    VJF_CUDA_OK(cudaEventRecord(h->ev_done[buf], ks));
+  }
+  VJF_CUDA_OK(cudaStreamSynchronize(ks));
+  VJF_CUDA_OK(cudaStreamSynchronize(cs));
+  return 0;
+}

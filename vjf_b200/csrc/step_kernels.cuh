@@ -1,0 +1,703 @@
+// Device code of the VJF filter + learning step (sm_100a).  Reference semantics: vjf/model.py:179-221.
+//
+//   phase A  (all CTAs, trial-parallel)  forward, one-sample ELBO, hand-derived backward, RLS statistics
+//            of a tile of trials; every CTA leaves its sums in its own slot of the partial buffer.
+//   phase B1 (all CTAs)  deterministic two-level reduction of the slots, gradient clip + SGD on the slice
+//            each CTA owns.
+//   phase B2 (CTA 0)     loss read-out, running noise variances, RLS: one augmented LDL^T sweep that yields
+//            chol(P'), L^-1 g and L^-T together, then W' = L^-T (L^-1 g).
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// tile GEMM helpers (SIMT fp32; rows is a multiple of 4, leading dimensions are multiples of 4)
+// ------------------------------------------------------------------------------------------
+
+// out[b][n] = act(bias[n] + sum_k A[b][k] W[k][n])      A: smem, W: global [K][N]
+__device__ __forceinline__ void tile_linear_fwd(const float* A, int lda, int K, const float* W, const float* bias, int N,
+                                                float* out, int ldo, int rows, bool do_tanh) {
+  const int items = N * (rows >> 2);
+  for (int it = threadIdx.x; it < items; it += VJF_NT) {
+    const int n = it % N, b0 = (it / N) << 2;
+    const float bv = bias ? bias[n] : 0.0f;
+    float acc0 = bv, acc1 = bv, acc2 = bv, acc3 = bv;
+    const float* a0 = A + b0 * lda;
+    const float* a1 = a0 + lda;
+    const float* a2 = a1 + lda;
+    const float* a3 = a2 + lda;
+    const float* w = W + n;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {
+      const float w0 = w[(size_t)k * N], w1 = w[(size_t)(k + 1) * N], w2 = w[(size_t)(k + 2) * N],
+                  w3 = w[(size_t)(k + 3) * N];
+      const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
+      const float4 x1 = *reinterpret_cast<const float4*>(a1 + k);
+      const float4 x2 = *reinterpret_cast<const float4*>(a2 + k);
+      const float4 x3 = *reinterpret_cast<const float4*>(a3 + k);
+      acc0 = fmaf(x0.x, w0, acc0); acc0 = fmaf(x0.y, w1, acc0); acc0 = fmaf(x0.z, w2, acc0); acc0 = fmaf(x0.w, w3, acc0);
+      acc1 = fmaf(x1.x, w0, acc1); acc1 = fmaf(x1.y, w1, acc1); acc1 = fmaf(x1.z, w2, acc1); acc1 = fmaf(x1.w, w3, acc1);
+      acc2 = fmaf(x2.x, w0, acc2); acc2 = fmaf(x2.y, w1, acc2); acc2 = fmaf(x2.z, w2, acc2); acc2 = fmaf(x2.w, w3, acc2);
+      acc3 = fmaf(x3.x, w0, acc3); acc3 = fmaf(x3.y, w1, acc3); acc3 = fmaf(x3.z, w2, acc3); acc3 = fmaf(x3.w, w3, acc3);
+    }
+    for (; k < K; ++k) {
+      const float wk = w[(size_t)k * N];
+      acc0 = fmaf(a0[k], wk, acc0); acc1 = fmaf(a1[k], wk, acc1); acc2 = fmaf(a2[k], wk, acc2); acc3 = fmaf(a3[k], wk, acc3);
+    }
+    if (do_tanh) { acc0 = tanhf(acc0); acc1 = tanhf(acc1); acc2 = tanhf(acc2); acc3 = tanhf(acc3); }
+    float* o = out + b0 * ldo + n;
+    o[0] = acc0; o[ldo] = acc1; o[2 * ldo] = acc2; o[3 * ldo] = acc3;
+  }
+}
+
+__device__ __forceinline__ void acc_store(float* p, float v, bool first) { *p = first ? v : (*p + v); }
+
+// dW[k][n] (+)= sum_b A[b][k] G[b][n]      A, G: smem; dW: this CTA's slot (global) [K][N]
+__device__ __forceinline__ void tile_wgrad(const float* A, int lda, int K, const float* G, int ldg, int N, int rows,
+                                           float* dW, bool first) {
+  const int kb = (K + 3) >> 2;
+  const int items = N * kb;
+  for (int it = threadIdx.x; it < items; it += VJF_NT) {
+    const int n = it % N, k0 = (it / N) << 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* ap = A + k0;
+    const float* gp = G + n;
+#pragma unroll 4
+    for (int b = 0; b < rows; ++b) {
+      const float4 x = *reinterpret_cast<const float4*>(ap + b * lda);
+      const float g = gp[b * ldg];
+      a0 = fmaf(x.x, g, a0); a1 = fmaf(x.y, g, a1); a2 = fmaf(x.z, g, a2); a3 = fmaf(x.w, g, a3);
+    }
+    float* o = dW + (size_t)k0 * N + n;
+    acc_store(o, a0, first);
+    if (k0 + 1 < K) acc_store(o + N, a1, first);
+    if (k0 + 2 < K) acc_store(o + 2 * N, a2, first);
+    if (k0 + 3 < K) acc_store(o + 3 * N, a3, first);
+  }
+}
+
+// db[n] (+)= sum_b G[b][n]
+__device__ __forceinline__ void tile_colsum(const float* G, int ldg, int N, int rows, float* db, bool first) {
+  for (int n = threadIdx.x; n < N; n += VJF_NT) {
+    float s = 0.f;
+    for (int b = 0; b < rows; ++b) s += G[b * ldg + n];
+    acc_store(db + n, s, first);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase A: one tile of trials
+// ------------------------------------------------------------------------------------------
+struct TileScal { float v[VJF_NSCAL]; };
+
+__device__ __forceinline__ float load_y(const StepParams& p, size_t idx) {
+  return p.y_dtype == VJF_Y_U8 ? (float)reinterpret_cast<const unsigned char*>(p.y)[idx]
+                               : reinterpret_cast<const float*>(p.y)[idx];
+}
+
+// masks: bit0 recon term on, bit1 dynamics term on (already combined with !warm_up), bit2 entropy term on
+static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
+  const int K1 = p.K1, K1p = p.K1p, Dp = p.Dp, Rp = p.Rp;
+  const int b0 = tile * p.TB;
+  const int nb = min(p.TB, p.B - b0);
+  const int rows = (nb + 3) & ~3;
+  float* in_s = sm + p.s_in;   float* g_s = sm + p.s_g;     float* phi_s = sm + p.s_phi;
+  float* gpa = sm + p.s_gpa;   float* gpb = sm + p.s_gpb;   float* eps_s = sm + p.s_eps;
+  float* xu_s = sm + p.s_xu;   float* xt_s = sm + p.s_xt;   float* mt_s = sm + p.s_mt;
+  float* lt_s = sm + p.s_lt;   float* pm_s = sm + p.s_pm;   float* dx_s = sm + p.s_dx;
+  float* gxt_s = sm + p.s_gxt; float* gmt_s = sm + p.s_gmt; float* glt_s = sm + p.s_glt;
+  float* plv_s = sm + p.s_plv; float* W_s = sm + p.s_W;     float* c_s = sm + p.s_c;
+  float* iw_s = sm + p.s_iw;   float* red_s = sm + p.s_red;
+  const float* U = p.U_in_smem ? (sm + p.s_U) : (p.state + p.lay.w_chol);
+  float* st = p.state;
+  float* slot = p.partials + (size_t)blockIdx.x * p.PS;
+  const bool r_on = masks & 1u, d_on = masks & 2u, h_on = masks & 4u;
+  const float lam = st[p.lay.lik_logvar], gam = st[p.lay.tr_logvar];
+  const float e_nlam = expf(-lam), e_ngam = expf(-gam), p_gam = expf(-0.5f * gam), p_lam = expf(-0.5f * lam);
+  float sc[VJF_NSCAL];
+#pragma unroll
+  for (int i = 0; i < VJF_NSCAL; ++i) sc[i] = 0.f;
+
+  // ---- S0: stage the tile: in = [y | u | m_s | l_s | 0] (vjf/recognition.py:32-37), eps, zero pads ----
+  {
+    const size_t ybase = ((size_t)t * p.B + b0) * D;
+    for (int i = tid; i < nb * D; i += VJF_NT) {
+      const int b = i / D, j = i - b * D;
+      in_s[b * K1p + j] = load_y(p, ybase + i);
+    }
+    const int Ep = K1p - D;  // u, m_s, l_s and the zero pad
+    const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
+    const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
+    const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
+    for (int i = tid; i < nb * Ep; i += VJF_NT) {
+      const int b = i / Ep, e = i - b * Ep;
+      float v = 0.f;
+      if (e < u) v = p.u_in[((size_t)t * p.B + b0 + b) * u + e];
+      else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
+      else if (e < E) v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
+      in_s[b * K1p + D + e] = v;
+    }
+    for (int i = tid; i < (rows - nb) * K1p; i += VJF_NT) in_s[nb * K1p + i] = 0.f;
+    if (p.eps) {
+      const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0) * d;
+      const float* e1 = e0 + (size_t)p.B * d;
+      for (int i = tid; i < nb * d; i += VJF_NT) {
+        const int b = i / d, k = i - b * d;
+        eps_s[b * 2 * d + k] = e0[i];
+        eps_s[b * 2 * d + d + k] = e1[i];
+      }
+    } else {
+      const int nblk = (d + 3) >> 2;
+      for (int i = tid; i < nb * 2 * nblk; i += VJF_NT) {
+        const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
+        float z[4];
+        philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
+        for (int k = 0; k < 4; ++k)
+          if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
+      }
+    }
+    // pad rows of everything that is summed over the rows of the tile
+    for (int i = tid; i < (rows - nb) * Rp; i += VJF_NT) phi_s[nb * Rp + i] = 0.f;
+    for (int i = tid; i < (rows - nb) * Dp; i += VJF_NT) g_s[nb * Dp + i] = 0.f;
+    for (int i = tid; i < (rows - nb) * p.Hpmax; i += VJF_NT) { gpa[nb * p.Hpmax + i] = 0.f; gpb[nb * p.Hpmax + i] = 0.f; }
+    for (int i = tid; i < (rows - nb) * d; i += VJF_NT) { dx_s[nb * d + i] = 0.f; gmt_s[nb * d + i] = 0.f; glt_s[nb * d + i] = 0.f; }
+  }
+  __syncthreads();
+
+  // ---- S1: xs = m_s + eps1 * exp(l_s / 2) (vjf/util.py:11-13); xu = [xs, u] (util.py:38-49) ----
+  for (int i = tid; i < nb * du; i += VJF_NT) {
+    const int b = i / du, k = i - b * du;
+    float v;
+    if (k < d) v = in_s[b * K1p + D + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * in_s[b * K1p + D + u + d + k]);
+    else v = in_s[b * K1p + D + (k - d)];
+    xu_s[b * du + k] = v;
+  }
+  __syncthreads();
+
+  // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
+  for (int i = tid; i < nb * Rp; i += VJF_NT) {
+    const int b = i / Rp, k = i - b * Rp;
+    float v = 0.f;
+    if (k < R) {
+      float d2 = 0.f;
+      for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
+      v = expf(d2 * iw_s[k]);
+    }
+    phi_s[b * Rp + k] = v;
+  }
+  __syncthreads();
+
+  // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
+  //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    float q = 0.f;
+    for (int k = lane; k < R; k += 32) {
+      float fl = 0.f;
+      const float* ph = phi_s + b * Rp;
+      for (int j = 0; j < R; ++j) fl = fmaf(ph[j], U[j * R + k], fl);
+      q = fmaf(fl, fl, q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) plv_s[b] = logf(q);
+  }
+  for (int i = tid; i < nb * d; i += VJF_NT) {
+    const int b = i / d, k = i - b * d;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s = fmaf(phi_s[b * Rp + r], W_s[r * d + k], s);
+    pm_s[i] = xu_s[b * du + k] + s;
+  }
+
+  // ---- S4: recognition MLP (vjf/recognition.py:31-42) ----
+  {
+    const float* A = in_s; int lda = K1p, K = K1;
+    for (int l = 0; l < L; ++l) {
+      float* out = sm + p.s_act[l];
+      tile_linear_fwd(A, lda, K, st + p.lay.mlp_w[l], st + p.lay.mlp_b[l], p.H[l], out, p.Hp[l], rows, true);
+      // zero the pad columns so float4 reads of this activation in the weight-gradient are finite
+      for (int i = tid; i < rows * (p.Hp[l] - p.H[l]); i += VJF_NT) {
+        const int b = i / (p.Hp[l] - p.H[l]), c = i - b * (p.Hp[l] - p.H[l]);
+        out[b * p.Hp[l] + p.H[l] + c] = 0.f;
+      }
+      __syncthreads();
+      A = out; lda = p.Hp[l]; K = p.H[l];
+    }
+    // heads: m_t = W_m h (no bias), l_t = W_v h + b_v ; then xt = m_t + eps2 exp(l_t/2), dx = xt - xs
+    const float* hL = A; const int HL = K, ldh = lda;
+    for (int i = tid; i < nb * d; i += VJF_NT) {
+      const int b = i / d, k = i - b * d;
+      float m = 0.f, lv = st[p.lay.head_v_b + k];
+      const float* wm = st + p.lay.head_m_w + k;
+      const float* wv = st + p.lay.head_v_w + k;
+      for (int n = 0; n < HL; ++n) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
+      mt_s[i] = m; lt_s[i] = lv;
+      const float x = m + eps_s[b * 2 * d + d + k] * expf(0.5f * lv);
+      xt_s[i] = x;
+      const float dxv = x - xu_s[b * du + k];
+      dx_s[i] = dxv;
+      sc[SC_SDX] = fmaf(dxv, dxv, sc[SC_SDX]);
+      // posterior of this step -> trajectory (returned by filter / fit, model.py:218-221, :305-307)
+      p.mu[((size_t)t * p.B + b0 + b) * d + k] = m;
+      p.logvar[((size_t)t * p.B + b0 + b) * d + k] = lv;
+    }
+  }
+  __syncthreads();
+
+  // ---- S5: decoder eta = D xt + bias (model.py:29-30), likelihood terms and dloss/deta (times B) ----
+  {
+    const float* dw = st + p.lay.dec_w;
+    const float* db = st + p.lay.dec_b;
+    for (int i = tid; i < nb * D; i += VJF_NT) {
+      const int b = i / D, j = i - b * D;
+      float eta = db[j];
+      for (int k = 0; k < d; ++k) eta = fmaf(dw[k * D + j], xt_s[b * d + k], eta);
+      const float yv = in_s[b * K1p + j];
+      float g;
+      if (p.lik == VJF_LIK_GAUSSIAN) {
+        // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
+        const float r = yv - eta;
+        const float rs = yv * p_lam - eta * p_lam;
+        const float mse = rs * rs;
+        if (!isfinite(mse)) sc[SC_BADMSE] += 1.f;
+        sc[SC_RECON] += 0.5f * (mse + lam);
+        sc[SC_SSE] = fmaf(r, r, sc[SC_SSE]);
+        g = -r * e_nlam;
+        // d/dlambda = 0.5 (1 - r^2 e^-lambda) ; accumulated into the lik_logvar gradient slot
+        sc[6] += r_on ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
+      } else {
+        // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62
+        const float ec = fminf(eta, 10.0f);
+        const float ex = expf(ec);
+        sc[SC_RECON] += ex - yv * ec;
+        g = (eta <= 10.0f) ? (ex - yv) : 0.f;
+        if (eta != eta) { sc[SC_RECON] = eta; g = eta; }  // NaN propagates like torch.clamp
+      }
+      g_s[b * Dp + j] = r_on ? g : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- S6: decoder gradients and g_xt = g_eta D ----
+  {
+    float* gdw = slot + p.lay.dec_w;
+    float* gdb = slot + p.lay.dec_b;
+    for (int j = tid; j < D; j += VJF_NT) {
+      float accb = 0.f, acc[VJF_MAX_XDIM];
+#pragma unroll
+      for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
+      for (int b = 0; b < nb; ++b) {
+        const float g = g_s[b * Dp + j];
+        accb += g;
+#pragma unroll
+        for (int k = 0; k < VJF_MAX_XDIM; ++k)
+          if (k < d) acc[k] = fmaf(g, xt_s[b * d + k], acc[k]);
+      }
+      acc_store(gdb + j, accb, first);
+#pragma unroll
+      for (int k = 0; k < VJF_MAX_XDIM; ++k)
+        if (k < d) acc_store(gdw + k * D + j, acc[k], first);
+    }
+    const float* dw = st + p.lay.dec_w;
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      float acc[VJF_MAX_XDIM];
+#pragma unroll
+      for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
+      for (int j = lane; j < D; j += 32) {
+        const float g = g_s[b * Dp + j];
+#pragma unroll
+        for (int k = 0; k < VJF_MAX_XDIM; ++k)
+          if (k < d) acc[k] = fmaf(g, dw[k * D + j], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < VJF_MAX_XDIM; ++k)
+        if (k < d) {
+          const float s = warp_sum(acc[k]);
+          if (lane == 0) gxt_s[b * d + k] = s;
+        }
+    }
+  }
+  __syncthreads();
+
+  // ---- S7: dynamics NLL (functional.py:55-75 via model.py:390-391), entropy (functional.py:25-29),
+  //      g_mt and g_lt (times B) ----
+  for (int i = tid; i < nb * d; i += VJF_NT) {
+    const int b = i / d, k = i - b * d;
+    const float m = mt_s[i], lv = lt_s[i], pm = pm_s[i], plv = plv_s[b];
+    const float e2 = eps_s[b * 2 * d + d + k], gx = gxt_s[i];
+    const float df = pm * p_gam - m * p_gam;
+    const float mse = df * df;
+    if (!isfinite(mse)) sc[SC_BADMSE] += 1.f;
+    const float tr = expf(plv + lv - gam);
+    sc[SC_DYN] += 0.5f * (mse + gam) + 0.5f * tr;
+    sc[SC_ENT] += 0.5f * lv;
+    float gm = gx, gl = 0.5f * gx * e2 * expf(0.5f * lv);
+    if (h_on) gl -= 0.5f;
+    if (d_on) { gm += (m - pm) * e_ngam; gl += 0.5f * tr; }
+    gmt_s[i] = gm; glt_s[i] = gl;
+  }
+  __syncthreads();
+
+  // ---- S8: backward through the heads and the MLP ----
+  {
+    const int HL = p.H[L - 1], ldh = p.Hp[L - 1];
+    const float* hL = sm + p.s_act[L - 1];
+    // head weight gradients [H_L][d] (input-major) and logvar-head bias
+    for (int i = tid; i < HL * d; i += VJF_NT) {
+      const int n = i / d, k = i - n * d;
+      float am = 0.f, av = 0.f;
+      for (int b = 0; b < nb; ++b) { const float h = hL[b * ldh + n]; am = fmaf(h, gmt_s[b * d + k], am); av = fmaf(h, glt_s[b * d + k], av); }
+      acc_store(slot + p.lay.head_m_w + i, am, first);
+      acc_store(slot + p.lay.head_v_w + i, av, first);
+    }
+    for (int k = tid; k < d; k += VJF_NT) {
+      float s = 0.f;
+      for (int b = 0; b < nb; ++b) s += glt_s[b * d + k];
+      acc_store(slot + p.lay.head_v_b + k, s, first);
+    }
+    // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2)
+    const float* wm = st + p.lay.head_m_w;
+    const float* wv = st + p.lay.head_v_w;
+    for (int i = tid; i < nb * HL; i += VJF_NT) {
+      const int b = i / HL, n = i - b * HL;
+      float s = 0.f;
+      for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], wm[n * d + k], s); s = fmaf(glt_s[b * d + k], wv[n * d + k], s); }
+      const float h = hL[b * ldh + n];
+      gpa[b * p.Hpmax + n] = s * (1.0f - h * h);
+    }
+    __syncthreads();
+    float* gcur = gpa; float* gnext = gpb;
+    for (int l = L - 1; l >= 0; --l) {
+      const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
+      const int ldp = (l == 0) ? K1p : p.Hp[l - 1];
+      const int Kl = (l == 0) ? K1 : p.H[l - 1];
+      tile_wgrad(Aprev, ldp, Kl, gcur, p.Hpmax, p.H[l], rows, slot + p.lay.mlp_w[l], first);
+      tile_colsum(gcur, p.Hpmax, p.H[l], rows, slot + p.lay.mlp_b[l], first);
+      if (l > 0) {
+        const float* Wl = st + p.lay.mlp_w[l];  // [Kl][H_l]
+        const int N = p.H[l];
+        for (int i = tid; i < nb * Kl; i += VJF_NT) {
+          const int b = i / Kl, k = i - b * Kl;
+          float s = 0.f;
+          for (int n = 0; n < N; ++n) s = fmaf(gcur[b * p.Hpmax + n], Wl[(size_t)k * N + n], s);
+          const float h = Aprev[b * ldp + k];
+          gnext[b * p.Hpmax + k] = s * (1.0f - h * h);
+        }
+        __syncthreads();
+        float* tmp = gcur; gcur = gnext; gnext = tmp;
+      }
+    }
+  }
+
+  // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
+  {
+    float* Ap = slot + p.pa;
+    const int kb = Rp >> 2;
+    for (int it = tid; it < R * kb; it += VJF_NT) {
+      const int kp = it % R, k0 = (it / R) << 2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int b = 0; b < rows; ++b) {
+        const float4 x = *reinterpret_cast<const float4*>(phi_s + b * Rp + k0);
+        const float g = phi_s[b * Rp + kp];
+        a0 = fmaf(x.x, g, a0); a1 = fmaf(x.y, g, a1); a2 = fmaf(x.z, g, a2); a3 = fmaf(x.w, g, a3);
+      }
+      float* o = Ap + (size_t)k0 * R + kp;
+      acc_store(o, a0, first);
+      if (k0 + 1 < R) acc_store(o + R, a1, first);
+      if (k0 + 2 < R) acc_store(o + 2 * R, a2, first);
+      if (k0 + 3 < R) acc_store(o + 3 * R, a3, first);
+    }
+    float* bp = slot + p.pb;
+    for (int i = tid; i < R * d; i += VJF_NT) {
+      const int r = i / d, k = i - r * d;
+      float s = 0.f;
+      for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r], dx_s[b * d + k], s);
+      acc_store(bp + i, s, first);
+    }
+  }
+
+  // ---- scalar sums of the tile ----
+#pragma unroll
+  for (int i = 0; i < VJF_NSCAL; ++i) {
+    const float s = warp_sum(sc[i]);
+    if (lane == 0) red_s[warp * VJF_NSCAL + i] = s;
+  }
+  __syncthreads();
+  if (tid < VJF_NSCAL) {
+    float s = 0.f;
+    for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
+    if (tid == 6) acc_store(slot + p.lay.lik_logvar, s, first);  // Gaussian d loss / d lambda (times B)
+    else acc_store(slot + p.ps + tid, s, first);
+  }
+  __syncthreads();
+}
+
+// Load the parameters every tile of this step shares into shared memory.
+static __device__ void phase_a_prologue(const StepParams& p, float* sm) {
+  const int tid = threadIdx.x;
+  const float* st = p.state;
+  float* W_s = sm + p.s_W; float* c_s = sm + p.s_c; float* iw_s = sm + p.s_iw;
+  for (int i = tid; i < p.R * p.d; i += VJF_NT) W_s[i] = st[p.lay.w_mean + i];
+  for (int i = tid; i < p.R * p.du; i += VJF_NT) c_s[i] = st[p.lay.centroid + i];
+  for (int i = tid; i < p.R; i += VJF_NT) { const float w = expf(st[p.lay.logwidth + i]); iw_s[i] = -0.5f / (w * w); }
+  if (p.U_in_smem) {
+    float* U_s = sm + p.s_U;
+    for (int i = tid; i < p.R * p.R; i += VJF_NT) U_s[i] = st[p.lay.w_chol + i];
+  }
+  __syncthreads();
+}
+
+static __device__ void phase_a(const StepParams& p, float* sm, int t, unsigned masks) {
+  phase_a_prologue(p, sm);
+  bool first = true;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    phase_a_tile(p, sm, t, tile, first, masks);
+    first = false;
+  }
+  if (first) {  // a CTA without tiles still owns a slot: zero it
+    float* slot = p.partials + (size_t)blockIdx.x * p.PS;
+    for (int i = threadIdx.x; i < p.PS; i += VJF_NT) slot[i] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase B1: reduce the slots (two-level, fixed order), clip + SGD on the owned slice
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sgd_applies(const StepParams& p, int e) {
+  if (!(p.flags & VJF_FLAG_SGD)) return false;
+  if (e == p.lay.lik_logvar) return p.lik == VJF_LIK_GAUSSIAN;
+  if ((p.flags & VJF_FLAG_DECODER_FROZEN) && e >= p.lay.dec_w && e < p.lay.dec_b + p.D) return false;
+  return e < p.lay.n_train;
+}
+
+// reduce `src` ([nslots][PS]) into p.reduced; when apply is set also take the SGD step (vjf/model.py:210-211)
+static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas) {
+  const int tid = threadIdx.x;
+  const int el = tid & 127, cg = tid >> 7;  // 128 elements x 4 slot groups per CTA pass
+  float* red4 = sm;                          // [4][128]
+  const int per = (nslots + 3) >> 2;
+  const int c0 = cg * per, c1 = min(nslots, c0 + per);
+  const float invB = 1.0f / (float)p.Bglobal;
+  for (int base = p.red_begin + cta * 128; base < p.PS; base += nctas * 128) {
+    const int e = base + el;
+    float s = 0.f;
+    if (e < p.PS) {
+      const float* q = src + e;
+      int c = c0;
+      for (; c + 3 < c1; c += 4) {
+        const float v0 = q[(size_t)c * p.PS], v1 = q[(size_t)(c + 1) * p.PS], v2 = q[(size_t)(c + 2) * p.PS],
+                    v3 = q[(size_t)(c + 3) * p.PS];
+        s += (v0 + v1) + (v2 + v3);
+      }
+      for (; c < c1; ++c) s += q[(size_t)c * p.PS];
+    }
+    red4[cg * 128 + el] = s;
+    __syncthreads();
+    if (cg == 0 && e < p.PS) {
+      const float tot = (red4[el] + red4[128 + el]) + (red4[256 + el] + red4[384 + el]);
+      p.reduced[e] = tot;
+      if (apply && sgd_applies(p, e)) p.state[e] -= p.lr * clip1(tot * invB);
+    }
+    __syncthreads();
+  }
+}
+
+// SGD from an already reduced vector (multi-GPU split path, after the all-reduce)
+static __device__ void sgd_from_reduced(const StepParams& p, int cta, int nctas) {
+  const float invB = 1.0f / (float)p.Bglobal;
+  for (int e = cta * VJF_NT + threadIdx.x; e < p.lay.n_train; e += nctas * VJF_NT)
+    if (sgd_applies(p, e)) p.state[e] -= p.lr * clip1(p.reduced[e] * invB);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase B2 (one CTA): losses, running variances, RLS
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float running_var_f(float acc_var, float acc_n, float new_var, float new_n, float cap,
+                                               float* n_out) {
+  // vjf/util.py:20-35 ; f1, f2 formed in double like the reference's Python floats, applied in fp32
+  const double a = fmin((double)acc_n, (double)cap), tot = a + (double)new_n;
+  const float f1 = (float)(a / tot), f2 = (float)((double)new_n / tot);
+  *n_out = (float)tot;
+  return f1 * acc_var + f2 * new_var;
+}
+
+static __device__ double block_sum_d(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < VJF_NWARP; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+
+// finmask: bit0 recon finite, bit1 dyn finite, bit2 entropy finite (from the reduced sums)
+static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned finmask) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = p.R, d = p.d, ldm = p.ldm;
+  float* st = p.state;
+  const float* red = p.reduced;
+  const float* A = red + p.pa;
+  const float* bv = red + p.pb;
+  const float* scal = red + p.ps;
+  const float Bf = (float)p.Bglobal;
+  const bool warm = p.flags & VJF_FLAG_WARMUP;
+  const bool upd = p.flags & VJF_FLAG_UPDATE;
+  float* M = sm;                                   // [(2R+d)][ldm]
+  float* dvec = sm + (size_t)(2 * R + d) * ldm;    // [R] pivots
+  const size_t doff = ((size_t)(2 * R + d) * ldm + ((R + 3) & ~3) + 5) & ~(size_t)1;  // 8-byte aligned
+  double* dred = reinterpret_cast<double*>(sm + doff);                          // [NWARP]
+
+  if (tid == 0 && !p.init_mode) {
+    unsigned stbits = 0;
+    float l_recon = scal[SC_RECON] / Bf, l_dyn = scal[SC_DYN] / Bf, h = scal[SC_ENT] / Bf;
+    if (!(finmask & 1u)) { l_recon = 0.f; stbits |= VJF_ST_RECON_NONFINITE; }
+    if (!(finmask & 2u)) { l_dyn = 0.f; stbits |= VJF_ST_DYN_NONFINITE; }
+    if (!(finmask & 4u)) { h = 0.f; stbits |= VJF_ST_ENTROPY_NONFINITE; }
+    if (scal[SC_BADMSE] != 0.f) stbits |= VJF_ST_MSE_NONFINITE;
+    float loss = l_recon - h;
+    if (!warm) loss += l_dyn;
+    if (p.losses) {
+      float* o = p.losses + (size_t)t * 4;
+      o[0] = loss; o[1] = -l_recon; o[2] = -l_dyn; o[3] = h;
+    }
+    if (stbits) atomicOr(p.status, stbits);
+    // GaussianLikelihood.update (vjf/likelihood.py:28-40): reads the post-SGD logvar
+    if (upd && p.lik == VJF_LIK_GAUSSIAN) {
+      const float mse = scal[SC_SSE] / (Bf * (float)p.D);
+      float n_new;
+      const float var = running_var_f(expf(st[p.lay.lik_logvar]), st[p.lay.lik_n], mse, Bf, 1000.f, &n_new);
+      st[p.lay.lik_logvar] = logf(var);
+      st[p.lay.lik_n] = n_new;
+    }
+  }
+  if (!upd) return;
+  const float gam = st[p.lay.tr_logvar];
+  // rls(x, target, v): v = exp(state logvar) in a filter step (model.py:371); in initialize v is the
+  // mean squared increment (model.py:384-385)
+  const float iv = p.init_mode ? (Bf * (float)d) / scal[SC_SDX] : 1.0f / expf(gam);
+  const float* P = st + p.lay.w_precision;
+  const float* Wold = st + p.lay.w_mean;
+
+  if (!warm) {
+    // ---- LinearRegression.rls (vjf/module.py:89-102) ----
+    // M rows [0,R): lower triangle of P' = P + A/v ; rows [R,R+d): g^T, g = P W + b/v ; rows [R+d,2R+d): I
+    for (int i = tid; i < R * R; i += VJF_NT) {
+      const int r = i / R, c = i - r * R;
+      if (c <= r) M[r * ldm + c] = fmaf(A[i], iv, P[i]);
+    }
+    for (int i = tid; i < R * d; i += VJF_NT) {
+      const int k = i / d, c = i - k * d;
+      float s = 0.f;
+      for (int j = 0; j < R; ++j) s = fmaf(P[k * R + j], Wold[j * d + c], s);
+      M[(R + c) * ldm + k] = fmaf(bv[i], iv, s);
+    }
+    for (int i = tid; i < R * R; i += VJF_NT) {
+      const int r = i / R, c = i - r * R;
+      M[(R + d + r) * ldm + c] = (r == c) ? 1.0f : 0.f;
+    }
+    __syncthreads();
+    // right-looking LDL^T sweep; appended rows receive the same eliminations, i.e. the forward substitutions
+    float piv = M[0];
+    float inv = 1.0f / piv;
+    bool fail = !(piv > 0.f);
+    for (int k = 0; k < R && !fail; ++k) {
+      if (tid == 0) dvec[k] = piv;
+      float pivn = 1.f;
+      if (k + 1 < R) {
+        const float l = M[(k + 1) * ldm + k];
+        pivn = fmaf(-(l * inv), l, M[(k + 1) * ldm + k + 1]);
+      }
+      const int rend = R + d + k + 1;
+      for (int r = k + 1 + warp; r < rend; r += VJF_NWARP) {
+        const float tk = M[r * ldm + k] * inv;
+        const int jend = (r < R) ? (r + 1) : R;
+        for (int j = k + 1 + lane; j < jend; j += 32) {
+          if (r == k + 1 && j == k + 1) continue;  // next pivot lives in registers
+          M[r * ldm + j] = fmaf(-tk, M[j * ldm + k], M[r * ldm + j]);
+        }
+      }
+      if (k + 1 < R && !(pivn > 0.f)) fail = true;
+      piv = pivn;
+      inv = 1.0f / pivn;
+      __syncthreads();
+    }
+    if (fail) {
+      if (tid == 0) { atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED); }
+    } else {
+      __syncthreads();
+      // scale: L = M D^-1/2 ; z = (L^-1 g)^T ; U = L^-T  (all columns k scaled by 1/sqrt(piv_k))
+      float* Lout = st + p.lay.w_pchol;
+      float* Uout = st + p.lay.w_chol;
+      float* Pout = st + p.lay.w_precision;
+      for (int i = tid; i < R * R; i += VJF_NT) {
+        const int r = i / R, c = i - r * R;
+        const float sd = sqrtf(dvec[c]);
+        Lout[i] = (c < r) ? M[r * ldm + c] / sd : ((c == r) ? sd : 0.f);
+        const float uv = (c >= r) ? M[(R + d + r) * ldm + c] / sd : 0.f;
+        Uout[i] = uv;
+        Pout[i] = fmaf(A[i], iv, P[i]);
+      }
+      for (int i = tid; i < R * d; i += VJF_NT) {
+        const int k = i / d, c = i - k * d;
+        M[(R + c) * ldm + k] = M[(R + c) * ldm + k] / sqrtf(dvec[k]);
+      }
+      __syncthreads();
+      // W' = U z : W'[r][c] = sum_{k>=r} U[r][k] z[c][k]
+      float* Wout = st + p.lay.w_mean;
+      for (int i = tid; i < R * d; i += VJF_NT) {
+        const int r = i / d, c = i - r * d;
+        float s = 0.f;
+        for (int k = r; k < R; ++k) s = fmaf(Uout[r * R + k], M[(R + c) * ldm + k], s);
+        Wout[i] = s;
+      }
+      __syncthreads();
+    }
+  }
+  (void)lane;
+
+  // ---- state-noise running variance (vjf/model.py:373-377).  sum |dx - phi W'|^2 from the reduced
+  //      statistics: S - 2 <W', b> + <W', A W'>, evaluated in double ----
+  {
+    const float* Wn = st + p.lay.w_mean;
+    double acc = 0.0;
+    for (int i = tid; i < R * R; i += VJF_NT) {
+      const int r = i / R, c = i - r * R;
+      double w2 = 0.0;
+      for (int k = 0; k < d; ++k) w2 += (double)Wn[r * d + k] * (double)Wn[c * d + k];
+      acc += (double)A[i] * w2;
+    }
+    for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)Wn[i] * (double)bv[i];
+    const double tot = block_sum_d(acc, dred) + (double)scal[SC_SDX];
+    if (tid == 0) {
+      const float mse = (float)(fmax(tot, 0.0) / ((double)p.Bglobal * (double)d));
+      if (p.init_mode) { st[p.lay.tr_logvar] = logf(mse); return; }  // model.py:387-388
+      float n_new;
+      const float var = running_var_f(expf(gam), st[p.lay.tr_n], mse, Bf, 500.f, &n_new);
+      st[p.lay.tr_logvar] = logf(var);
+      st[p.lay.tr_n] = n_new;
+    }
+  }
+}
+
+// finite flags of the three ELBO terms from the slots (every CTA evaluates this identically)
+static __device__ unsigned term_finite_mask(const StepParams& p, const float* src, int nslots, float* sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned* flag = reinterpret_cast<unsigned*>(sm);
+  if (warp == 0) {
+    unsigned m = 0;
+    for (int i = 0; i < 3; ++i) {
+      float s = 0.f;
+      for (int c = lane; c < nslots; c += 32) s += src[(size_t)c * p.PS + p.ps + i];
+      s = warp_sum(s);
+      if (isfinite(s)) m |= 1u << i;
+    }
+    if (lane == 0) *flag = m;
+  }
+  __syncthreads();
+  const unsigned m = *flag;
+  __syncthreads();
+  return m;
+}
