@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the VJF filter + learning step (BASELINE.json metric: trial-steps/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): Lorenz attractor latent, xdim=3, ydim=200 Poisson, 50 RBF
+centers, hidden [64], 4096 parallel trials per GPU, T=256 time steps per bench step.  One bench "step"
+= one pass of the time loop of VJF.fit (one epoch: T filter+learning steps, sgd=True, update=True,
+warm_up=False) over the synthetic batch = B*T trial-steps.
+
+  value     device-resident inputs, CUDA-event timed, max over ranks
+  e2e       same work through the C ABI entry vjf_run_host with PINNED HOST buffers: host->device
+            copies of the observations and device->host copies of trajectory + losses inside the timed region
+  roofline  algorithmic HBM bytes of the persistent step kernel / its measured duration vs the measured
+            copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the numpy oracle (a port of the reference's algorithm) on the host cores, bounded sample
+
+--impl reference times the CPU implementation of the same path (the oracle port; the reference is pure
+Python and is not present on the GPU box) on the same workload, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[64], likelihood="poisson",
+          trials_per_gpu=4096, T=256)
+ALGO_BYTES_PER_TRIAL_STEP = lambda c, y_bytes=4: y_bytes * c["ydim"] + 4 * (c["udim"] + 4 * c["xdim"])
+
+
+# ------------------------------------------------------------------------------------------------
+def lorenz_poisson(T, B, D, seed, device=None):
+    """Synthetic data of SURVEY.md section 8d row C2: Lorenz (sigma=10, rho=28, beta=8/3, RK4 dt=0.01),
+    per-trial random initial state, z-scored; C ~ N(0,1)/sqrt(3), b=-1; y ~ Poisson(exp(xC+b))."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, 3, generator=g, dtype=torch.float64) * 5 + torch.tensor([0., 0., 25.], dtype=torch.float64)
+    C = (torch.randn(3, D, generator=g, dtype=torch.float64) / 3 ** 0.5)
+    if device is not None:
+        x, C = x.to(device), C.to(device)
+
+    def f(s):
+        return torch.stack((10 * (s[:, 1] - s[:, 0]), s[:, 0] * (28 - s[:, 2]) - s[:, 1], s[:, 0] * s[:, 1] - 8 / 3 * s[:, 2]), -1)
+
+    dt, burn = 0.01, 200
+    xs = []
+    for t in range(burn + T):
+        k1 = f(x); k2 = f(x + 0.5 * dt * k1); k3 = f(x + 0.5 * dt * k2); k4 = f(x + dt * k3)
+        x = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        if t >= burn:
+            xs.append(x)
+    xs = torch.stack(xs)  # (T,B,3)
+    xs = (xs - xs.mean((0, 1))) / xs.std((0, 1))
+    rate = torch.exp(torch.clamp(xs @ C - 1.0, max=4.0))
+    gy = torch.Generator(device=rate.device).manual_seed(seed + 1)
+    y = torch.poisson(rate.float(), generator=gy)
+    return y  # float32 counts (T,B,D)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(cfg, B, T_sample, seed=0, y=None):
+    """trial-steps/s of the numpy oracle (reference algorithm port) on a bounded sample."""
+    from oracle.vjf_oracle import OracleVJF
+    rng = np.random.default_rng(seed)
+    o = OracleVJF(cfg["ydim"], cfg["xdim"], cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], dtype=np.float32)
+    if y is None:
+        y = rng.poisson(0.5, (T_sample, B, cfg["ydim"])).astype(np.float32)
+    eps = rng.normal(size=(T_sample + 1, 2, B, cfg["xdim"])).astype(np.float32)
+    o.run(y[:1], None, eps=eps[:1])  # warm the BLAS threads / allocator
+    t0 = time.perf_counter()
+    o.run(y[:T_sample], None, eps=eps[1:])
+    dt = time.perf_counter() - t0
+    return B * T_sample / dt, dt
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = cfg["trials_per_gpu"] * args.gpus  # whole-job batch on the host cores
+    cores = os.cpu_count()
+    T_s = max(1, args.ref_steps_per_step)
+    rng = np.random.default_rng(0)
+    y = rng.poisson(0.5, (T_s, B, cfg["ydim"])).astype(np.float32)
+    for _ in range(args.warmup):
+        cpu_port_rate(cfg, B, 1, y=y)
+    t0 = time.perf_counter()
+    rates = [cpu_port_rate(cfg, B, T_s, seed=i, y=y)[0] for i in range(args.steps)]
+    wall = time.perf_counter() - t0
+    val = float(np.mean(rates))
+    out = {"impl": "reference", "metric": "trial-steps/sec", "value": val, "unit": "trial-steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(cfg, args.gpus, T_override=T_s),
+           "cpu_baseline": {"value": val, "unit": "trial-steps/s", "cores": cores, "kind": "port",
+                            "sample": f"{T_s} time steps x {B} trials per bench step, numpy/OpenBLAS oracle port of vjf/model.py:179-221"},
+           "e2e": {"value": val, "unit": "trial-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(cfg, n_gpus, T_override=None):
+    return {"workload": f"{cfg['name']}: xdim={cfg['xdim']} ydim={cfg['ydim']} {cfg['likelihood']} n_rbf={cfg['n_rbf']} "
+                        f"hidden={cfg['hidden']} trials={cfg['trials_per_gpu']}/GPU x {n_gpus} GPU, "
+                        f"T={T_override or cfg['T']} time steps per bench step (sgd=True, update=True, warm_up=False)",
+            "trials_per_gpu": cfg["trials_per_gpu"], "global_trials": cfg["trials_per_gpu"] * n_gpus,
+            "time_steps_per_step": T_override or cfg["T"], "parallelism": f"trial-sharded x{n_gpus}",
+            "l2_policy": "inputs larger than L2 (observations of one bench step = %.0f MB/GPU)" %
+                         (cfg["trials_per_gpu"] * (T_override or cfg["T"]) * cfg["ydim"] * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from vjf_b200 import _lib
+    from vjf_b200.model import VJF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, D, d = cfg["trials_per_gpu"], cfg["T"], cfg["ydim"], cfg["xdim"]
+    lib = _lib.load()
+
+    torch.manual_seed(1234)  # identical parameters on every rank
+    model = VJF.make_model(D, d, cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], max_trials=B, seed=99, device=dev)
+    y_dev = lorenz_poisson(T, B, D, seed=1000 + rank, device=dev).contiguous()
+    y_host = y_dev.cpu().pin_memory()
+    mu_h = torch.empty(T, B, d).pin_memory(); lv_h = torch.empty(T, B, d).pin_memory(); ls_h = torch.empty(T, 4).pin_memory()
+
+    if world > 1:
+        from vjf_b200.distributed import ShardedVJF
+        runner = ShardedVJF(model)
+        step_dev = lambda: runner.run(y_dev)
+        step_e2e = lambda: runner.run_host(y_host, mu_h, lv_h, ls_h)
+    else:
+        step_dev = lambda: model.run(y_dev)
+        flags = _lib.FLAG_SGD | _lib.FLAG_UPDATE | _lib.FLAG_PRIOR_Q0
+        p = lambda t: C.c_void_p(t.data_ptr())
+
+        def step_e2e():
+            _lib.check(lib.vjf_run_host(model._h, T, B, p(y_host), _lib.Y_F32, None, None, model.seed, model._step_index, flags,
+                                        model.lr, p(mu_h), p(lv_h), p(ls_h), args.chunk))
+            model._step_index += T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also brings the clocks up from idle) ----
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    torch.cuda.synchronize()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < args.spinup:
+        step_dev()
+        torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.vjf_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for a, b in evs:
+        a.record(); step_dev(); b.record()
+    t1.record()
+    barrier()
+    launches = lib.vjf_launch_count() - launches0
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.stop()
+    status = model.status()
+
+    # ---- timed region: end to end through the C ABI with pinned host buffers ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+
+    if world > 1:
+        tt = torch.tensor([total_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, kern_ms = tt.tolist()
+
+    if rank == 0:
+        units = B * world * T * args.steps
+        value = units / (total_ms * 1e-3)
+        peak, peak_src = measured_peak_gbs()
+        algo_bytes = ALGO_BYTES_PER_TRIAL_STEP(cfg) * B * T  # per launch of the persistent kernel, per GPU
+        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        out = {"metric": "trial-steps/sec", "value": value, "unit": "trial-steps/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic (Lorenz-driven Poisson counts, random-init parameters)",
+               "config": workload_config(cfg, world),
+               "us_per_time_step": total_ms / args.steps / T * 1e3,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "kernel": "vjf_persistent_kernel" if world == 1 else "vjf_phase_a_kernel+vjf_phase_b_kernel",
+                            "algorithmic_bytes_per_trial_step": ALGO_BYTES_PER_TRIAL_STEP(cfg), "peak_source": peak_src,
+                            "note": "B=4096 trials/step is latency-bound by the per-step serial chain (grid barriers + RLS factorisation), see DESIGN.md"},
+               "e2e": {"value": units / e2e_s, "unit": "trial-steps/s", "h2d_bytes_per_step": int(y_host.numel() * 4),
+                       "d2h_bytes_per_step": int((mu_h.numel() + lv_h.numel() + ls_h.numel()) * 4),
+                       "api": "vjf_run_host (C ABI, pinned host buffers, chunked H2D overlapped with compute)"},
+               "gpu_launches": int(launches), "clocks": clocks, "status_word": int(status)}
+        if world == 1 and not args.no_cpu:
+            val, dt = cpu_port_rate(cfg, B, args.cpu_steps)
+            out["cpu_baseline"] = {"value": val, "unit": "trial-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{args.cpu_steps} time steps x {B} trials ({dt:.1f} s), numpy/OpenBLAS oracle port of vjf/model.py:179-221"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trials", type=int, default=None, help="trials per GPU (default: the C2 workload, 4096)")
+    ap.add_argument("--T", type=int, default=None, help="time steps per bench step (default 256)")
+    ap.add_argument("--chunk", type=int, default=32, help="time steps per H2D chunk in the e2e path")
+    ap.add_argument("--spinup", type=float, default=1.0, help="seconds of extra untimed load so clocks leave idle")
+    ap.add_argument("--cpu-steps", type=int, default=200, help="time steps of the CPU baseline sample (~10-20 s)")
+    ap.add_argument("--ref-steps-per-step", type=int, default=16, help="--impl reference: time steps per bench step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(C2)
+    if args.trials:
+        cfg["trials_per_gpu"] = args.trials
+    if args.T:
+        cfg["T"] = args.T
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

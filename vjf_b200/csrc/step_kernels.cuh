@@ -473,21 +473,32 @@ __device__ __forceinline__ bool sgd_applies(const StepParams& p, int e) {
 // reduce `src` ([nslots][PS]) into p.reduced; when apply is set also take the SGD step (vjf/model.py:210-211)
 static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas) {
   const int tid = threadIdx.x;
+  const float invB = 1.0f / (float)p.Bglobal;
+  if (nslots < 16) {
+    // few slots (small batches): one thread per element, slots summed in order
+    for (int e = p.red_begin + cta * VJF_NT + tid; e < p.PS; e += nctas * VJF_NT) {
+      float tot = 0.f;
+      for (int c = 0; c < nslots; ++c) tot += src[(size_t)c * p.PS + e];
+      p.reduced[e] = tot;
+      if (apply && sgd_applies(p, e)) p.state[e] -= p.lr * clip1(tot * invB);
+    }
+    return;
+  }
   const int el = tid & 127, cg = tid >> 7;  // 128 elements x 4 slot groups per CTA pass
   float* red4 = sm;                          // [4][128]
   const int per = (nslots + 3) >> 2;
   const int c0 = cg * per, c1 = min(nslots, c0 + per);
-  const float invB = 1.0f / (float)p.Bglobal;
   for (int base = p.red_begin + cta * 128; base < p.PS; base += nctas * 128) {
     const int e = base + el;
     float s = 0.f;
     if (e < p.PS) {
       const float* q = src + e;
       int c = c0;
-      for (; c + 3 < c1; c += 4) {
-        const float v0 = q[(size_t)c * p.PS], v1 = q[(size_t)(c + 1) * p.PS], v2 = q[(size_t)(c + 2) * p.PS],
-                    v3 = q[(size_t)(c + 3) * p.PS];
-        s += (v0 + v1) + (v2 + v3);
+      for (; c + 7 < c1; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = q[(size_t)(c + i) * p.PS];
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
       }
       for (; c < c1; ++c) s += q[(size_t)c * p.PS];
     }

@@ -1,0 +1,97 @@
+"""Trials sharded over the GPUs of one node: one process per GPU, parameters and RLS state replicated.
+
+Per time step every rank runs phase A on its own trials (vjf_step_phase_a), the packed vector of local
+sums -- SGD gradients, RLS statistics phi^T phi / phi^T dx, loss sums -- is all-reduced once over
+NCCL/NVLink (the only exchange of the step), and every rank applies the identical
+phase B (clip + SGD, running variances, RLS factorisation) so the replicas stay in lock-step without a
+broadcast.  The gradient clip is applied after the reduction, as the reference clips the batch-mean
+gradient (vjf/model.py:210).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .model import VJF, Gaussian
+
+
+class _DevBuf:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def shard_bounds(n_trials: int, world: int, rank: int):
+    """Contiguous block partition of the trial axis (the last ranks get the smaller blocks)."""
+    per = (n_trials + world - 1) // world
+    lo = min(n_trials, rank * per)
+    return lo, min(n_trials, lo + per)
+
+
+def plan_step(t: int, sgd=True, update=True, warm_up=False, decoder_frozen=False):
+    f = 0
+    if sgd:
+        f |= _lib.FLAG_SGD
+    if update:
+        f |= _lib.FLAG_UPDATE
+    if warm_up:
+        f |= _lib.FLAG_WARMUP
+    if decoder_frozen:
+        f |= _lib.FLAG_DECODER_FROZEN
+    if t == 0:
+        f |= _lib.FLAG_PRIOR_Q0
+    return f
+
+
+class ShardedVJF:
+    def __init__(self, model: VJF, group=None):
+        self.m = model
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lib = model._lib
+        n = int(lib.vjf_reduce_size(model._h))
+        ptr = lib.vjf_reduce_buffer(model._h)
+        self.reduce_buf = torch.as_tensor(_DevBuf(ptr, n), device=model.device)
+
+    @torch.no_grad()
+    def run(self, y, u=None, *, sgd=True, update=True, warm_up=False, eps=None, trial_offset=None):
+        """y: (T, B_local, ydim) on this rank's device.  Returns mu, logvar (T, B_local, d), losses (T, 4)
+        (losses are whole-job values, identical on every rank)."""
+        m, lib = self.m, self.m._lib
+        y = y if y.dtype == torch.uint8 else y.to(m.device, torch.float32)
+        ydt = _lib.Y_U8 if y.dtype == torch.uint8 else _lib.Y_F32
+        T, B, _ = y.shape
+        nb = torch.tensor([B], device=m.device)
+        if self.world > 1:
+            dist.all_reduce(nb, group=self.group)
+        Bg = int(nb.item())
+        off = self.rank * B if trial_offset is None else trial_offset
+        mu = torch.empty(T, B, m.xdim, device=m.device)
+        lv = torch.empty_like(mu)
+        losses = torch.empty(T, 4, device=m.device)
+        frozen = not m.decoder.decode.weight.requires_grad
+        p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        s = m._stream()
+        for t in range(T):
+            f = plan_step(t, sgd, update, warm_up, frozen)
+            _lib.check(lib.vjf_step_phase_a(m._h, B, Bg, p(y[t]), ydt, p(None if u is None else u[t]),
+                                            p(None if t == 0 else mu[t - 1]), p(None if t == 0 else lv[t - 1]),
+                                            p(None if eps is None else eps[t]), m.seed, m._step_index + t, off, f,
+                                            p(mu[t]), p(lv[t]), s))
+            if self.world > 1:
+                dist.all_reduce(self.reduce_buf, group=self.group)
+            _lib.check(lib.vjf_step_phase_b(m._h, Bg, f, m.lr, p(losses[t]), s))
+        m._step_index += T
+        return mu, lv, losses
+
+    @torch.no_grad()
+    def run_host(self, y_host, mu_host, lv_host, losses_host):
+        y = y_host.to(self.m.device, non_blocking=True)
+        mu, lv, losses = self.run(y)
+        mu_host.copy_(mu, non_blocking=True); lv_host.copy_(lv, non_blocking=True); losses_host.copy_(losses, non_blocking=True)
+        torch.cuda.synchronize()
