@@ -28,6 +28,7 @@ struct StepParams {
   // ---- dimensions ----
   int B, Bglobal, D, d, u, R, L, H[VJF_MAX_LAYERS];
   int K1, K1p, E, du, Dp, Rp, Hp[VJF_MAX_LAYERS], Hpmax;
+  int Gp, ldu;         // row strides of the g_pre buffers and of the staged w_chol
   int lik;
   Lay lay;
   // ---- partial-sum vector layout: [0,G) grads | A (R*R) | b (R*d) | scalars ----
@@ -36,8 +37,8 @@ struct StepParams {
   int TB, ntiles, nslots;
   // ---- shared-memory plan (float offsets) ----
   int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
-      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_total;
-  int U_in_smem;
+      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_total;
+  int U_in_smem, dec_in_smem;
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
   float* state;

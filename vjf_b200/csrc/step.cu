@@ -139,49 +139,63 @@ static void lay_to_int(const vjf_layout& a, Lay& b) {
   b.total = (int)a.total;
 }
 
-// shared-memory plan for a tile of `tb` rows; returns the number of floats (phase A vs phase B2 maximum)
-static size_t plan_smem(StepParams& p, int tb, bool u_in_smem) {
+// smallest x >= lo with x % 32 == tgt (tgt is a multiple of 4): bank-conflict-free fragment strides
+static int pad_mod32(int lo, int tgt) {
+  int x = (lo / 32) * 32 + tgt;
+  while (x < lo) x += 32;
+  return x;
+}
+
+// shared-memory plan for a tile of `tb` trials (rows padded to a multiple of 16 for the MMA tiles);
+// returns the number of floats (maximum over phase A, B1 and B2)
+static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem) {
+  const int rows = (tb + 15) & ~15;
   size_t off = 0;
   auto take = [&](size_t n) { size_t at = off; off = (off + n + 3) & ~(size_t)3; return (int)at; };
-  p.s_in = take((size_t)tb * p.K1p);
-  p.s_g = take((size_t)tb * p.Dp);
-  p.s_phi = take((size_t)tb * p.Rp);
-  for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)tb * p.Hp[l]);
-  p.s_gpa = take((size_t)tb * p.Hpmax);
-  p.s_gpb = take((size_t)tb * p.Hpmax);
-  p.s_eps = take((size_t)tb * 2 * p.d);
-  p.s_xu = take((size_t)tb * p.du);
-  p.s_xt = take((size_t)tb * p.d); p.s_mt = take((size_t)tb * p.d); p.s_lt = take((size_t)tb * p.d);
-  p.s_pm = take((size_t)tb * p.d); p.s_dx = take((size_t)tb * p.d); p.s_gxt = take((size_t)tb * p.d);
-  p.s_gmt = take((size_t)tb * p.d); p.s_glt = take((size_t)tb * p.d); p.s_plv = take((size_t)tb);
+  p.s_in = take((size_t)rows * p.K1p);
+  p.s_g = take((size_t)rows * p.Dp);
+  p.s_phi = take((size_t)rows * p.Rp);
+  for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)rows * p.Hp[l]);
+  p.s_gpa = take((size_t)rows * p.Gp);
+  p.s_gpb = take((size_t)rows * p.Gp);
+  p.s_eps = take((size_t)rows * 2 * p.d);
+  p.s_xu = take((size_t)rows * p.du);
+  p.s_xt = take((size_t)rows * p.d); p.s_mt = take((size_t)rows * p.d); p.s_lt = take((size_t)rows * p.d);
+  p.s_pm = take((size_t)rows * p.d); p.s_dx = take((size_t)rows * p.d); p.s_gxt = take((size_t)rows * p.d);
+  p.s_gmt = take((size_t)rows * p.d); p.s_glt = take((size_t)rows * p.d); p.s_plv = take((size_t)rows);
+  p.s_qp = take((size_t)((p.R + 7) / 8) * 32 + 32);
   p.U_in_smem = u_in_smem ? 1 : 0;
-  p.s_U = take(u_in_smem ? (size_t)p.R * p.R : 0);
+  p.s_U = take(u_in_smem ? (size_t)((p.R + 7) & ~7) * p.ldu : 0);
+  p.dec_in_smem = dec_in_smem ? 1 : 0;
+  p.s_dec = take(dec_in_smem ? (size_t)(p.d + 1) * p.D : 0);
   p.s_W = take((size_t)p.R * p.d);
   p.s_c = take((size_t)p.R * p.du);
   p.s_iw = take((size_t)p.R);
   p.s_red = take((size_t)VJF_NWARP * VJF_NSCAL + 64);
   const size_t a = off;
-  // phase B2: [(2R+d)][ldm] + pivots + double scratch ; phase B1: 512 floats
-  const size_t b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
+  // phase B2: register path needs ~2(2R+d) + R + 2dR floats; the shared-memory fallback (R > 128)
+  // [(2R+d)][ldm] + pivots; phase B1: 512 floats
+  size_t b2 = 2 * (size_t)(2 * p.R + p.d + 4) + p.R + 4 + 2 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
+  if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
   p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
   return (size_t)p.s_total;
 }
 
 static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots) {
   if (B < 1 || B > h->cfg.max_trials) { vjf_set_error("trials B=%d outside [1, max_trials=%d]", B, h->cfg.max_trials); return -1; }
-  int tb = (int)up((B + max_slots - 1) / max_slots, 4);
-  tb = std::min(std::max(tb, 4), VJF_TB_MAX);
+  const int want = std::min(std::max((int)up((B + max_slots - 1) / max_slots, 4), 4), VJF_TB_MAX);
   const size_t limit = h->smem_limit;
-  bool u_smem = (size_t)p.R * p.R * 4 <= 96 * 1024;
+  bool u_smem = (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
+  bool dec_smem = (size_t)(p.d + 1) * p.D * 4 <= 32 * 1024;
+  int tb = want;
   for (;;) {
-    if (plan_smem(p, tb, u_smem) * 4 <= limit) break;
+    if (plan_smem(p, tb, u_smem, dec_smem) * 4 <= limit) break;
     if (tb > 4) { tb -= 4; continue; }
-    if (u_smem) { u_smem = false; tb = std::min(std::max((int)up((B + max_slots - 1) / max_slots, 4), 4), VJF_TB_MAX); continue; }
+    if (dec_smem) { dec_smem = false; tb = want; continue; }
+    if (u_smem) { u_smem = false; tb = want; continue; }
     vjf_set_error("configuration does not fit in %zu bytes of shared memory (ydim=%d n_rbf=%d)", limit, p.D, p.R);
     return -1;
   }
-  const size_t b2 = ((size_t)(2 * p.R + p.d) * p.ldm + p.R + 64) * 4;
-  if (b2 > limit) { vjf_set_error("n_rbf=%d too large for the single-CTA RLS factorisation of this build", p.R); return -1; }
   p.B = B;
   p.TB = tb;
   p.ntiles = (B + tb - 1) / tb;
@@ -220,10 +234,21 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   StepParams& p = h->base;
   memset(&p, 0, sizeof(p));
   p.D = cfg->ydim; p.d = cfg->xdim; p.u = cfg->udim; p.R = cfg->n_rbf; p.L = cfg->n_layers;
-  p.K1 = p.D + p.u + 2 * p.d; p.K1p = (int)up(p.K1, 4); p.E = p.u + 2 * p.d; p.du = p.d + p.u;
-  p.Dp = (int)up(p.D, 4); p.Rp = (int)up(p.R, 4);
+  p.K1 = p.D + p.u + 2 * p.d; p.E = p.u + 2 * p.d; p.du = p.d + p.u;
+  // strides chosen so that the mma fragment loads are bank-conflict free (see mma.cuh)
+  p.K1p = pad_mod32((int)up(p.K1, 16), 4);
+  p.Dp = (int)up(p.D, 4);
+  p.Rp = pad_mod32((int)up(p.R, 16), 4);
+  p.ldu = pad_mod32((int)up(p.R, 8), 8);
   p.Hpmax = 4;
-  for (int l = 0; l < p.L; ++l) { p.H[l] = cfg->hidden[l]; p.Hp[l] = (int)up(p.H[l], 4); p.Hpmax = std::max(p.Hpmax, p.Hp[l]); }
+  int hmax = 1;
+  for (int l = 0; l < p.L; ++l) {
+    p.H[l] = cfg->hidden[l];
+    p.Hp[l] = pad_mod32((int)up(p.H[l], 16), 4);
+    p.Hpmax = std::max(p.Hpmax, p.Hp[l]);
+    hmax = std::max(hmax, p.H[l]);
+  }
+  p.Gp = pad_mod32((int)up(hmax, 8), 8);
   p.lik = cfg->likelihood;
   lay_to_int(lay, p.lay);
   p.G = p.lay.n_train;

@@ -8,6 +8,7 @@
 //            chol(P'), L^-1 g and L^-T together, then W' = L^-T (L^-1 g).
 #pragma once
 #include "common.cuh"
+#include "mma.cuh"
 
 // ------------------------------------------------------------------------------------------
 // tile GEMM helpers (SIMT fp32; rows is a multiple of 4, leading dimensions are multiples of 4)
@@ -87,30 +88,29 @@ __device__ __forceinline__ void tile_colsum(const float* G, int ldg, int N, int 
 // ------------------------------------------------------------------------------------------
 // phase A: one tile of trials
 // ------------------------------------------------------------------------------------------
-struct TileScal { float v[VJF_NSCAL]; };
-
 __device__ __forceinline__ float load_y(const StepParams& p, size_t idx) {
   return p.y_dtype == VJF_Y_U8 ? (float)reinterpret_cast<const unsigned char*>(p.y)[idx]
                                : reinterpret_cast<const float*>(p.y)[idx];
 }
 
 // masks: bit0 recon term on, bit1 dynamics term on (already combined with !warm_up), bit2 entropy term on
-static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks) {
+static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int u_upper) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
-  const int K1 = p.K1, K1p = p.K1p, Dp = p.Dp, Rp = p.Rp;
+  const int K1 = p.K1, K1p = p.K1p, Dp = p.Dp, Rp = p.Rp, Gp = p.Gp;
   const int b0 = tile * p.TB;
   const int nb = min(p.TB, p.B - b0);
-  const int rows = (nb + 3) & ~3;
+  const int rows = (nb + 15) & ~15;
   float* in_s = sm + p.s_in;   float* g_s = sm + p.s_g;     float* phi_s = sm + p.s_phi;
   float* gpa = sm + p.s_gpa;   float* gpb = sm + p.s_gpb;   float* eps_s = sm + p.s_eps;
   float* xu_s = sm + p.s_xu;   float* xt_s = sm + p.s_xt;   float* mt_s = sm + p.s_mt;
   float* lt_s = sm + p.s_lt;   float* pm_s = sm + p.s_pm;   float* dx_s = sm + p.s_dx;
   float* gxt_s = sm + p.s_gxt; float* gmt_s = sm + p.s_gmt; float* glt_s = sm + p.s_glt;
   float* plv_s = sm + p.s_plv; float* W_s = sm + p.s_W;     float* c_s = sm + p.s_c;
-  float* iw_s = sm + p.s_iw;   float* red_s = sm + p.s_red;
-  const float* U = p.U_in_smem ? (sm + p.s_U) : (p.state + p.lay.w_chol);
+  float* iw_s = sm + p.s_iw;   float* red_s = sm + p.s_red; float* qp_s = sm + p.s_qp;
   float* st = p.state;
+  const float* dw = p.dec_in_smem ? (sm + p.s_dec) : (st + p.lay.dec_w);        // [d][D]
+  const float* db = p.dec_in_smem ? (sm + p.s_dec + d * D) : (st + p.lay.dec_b);  // [D]
   float* slot = p.partials + (size_t)blockIdx.x * p.PS;
   const bool r_on = masks & 1u, d_on = masks & 2u, h_on = masks & 4u;
   const float lam = st[p.lay.lik_logvar], gam = st[p.lay.tr_logvar];
@@ -121,47 +121,57 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
 
   // ---- S0: stage the tile: in = [y | u | m_s | l_s | 0] (vjf/recognition.py:32-37), eps, zero pads ----
   {
-    const size_t ybase = ((size_t)t * p.B + b0) * D;
-    for (int i = tid; i < nb * D; i += VJF_NT) {
-      const int b = i / D, j = i - b * D;
-      in_s[b * K1p + j] = load_y(p, ybase + i);
-    }
+    const size_t row0 = (size_t)t * p.B + b0;
     const int Ep = K1p - D;  // u, m_s, l_s and the zero pad
     const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
     const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
     const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-    for (int i = tid; i < nb * Ep; i += VJF_NT) {
-      const int b = i / Ep, e = i - b * Ep;
-      float v = 0.f;
-      if (e < u) v = p.u_in[((size_t)t * p.B + b0 + b) * u + e];
-      else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
-      else if (e < E) v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
-      in_s[b * K1p + D + e] = v;
-    }
-    for (int i = tid; i < (rows - nb) * K1p; i += VJF_NT) in_s[nb * K1p + i] = 0.f;
-    if (p.eps) {
-      const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0) * d;
-      const float* e1 = e0 + (size_t)p.B * d;
-      for (int i = tid; i < nb * d; i += VJF_NT) {
-        const int b = i / d, k = i - b * d;
-        eps_s[b * 2 * d + k] = e0[i];
-        eps_s[b * 2 * d + d + k] = e1[i];
+    for (int b = warp; b < rows; b += VJF_NWARP) {
+      float* dst = in_s + b * K1p;
+      if (b < nb) {
+        if ((D & 3) == 0) {
+          if (p.y_dtype == VJF_Y_U8) {
+            const uchar4* src = reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(p.y) + (row0 + b) * D);
+            for (int j = lane; j < (D >> 2); j += 32) {
+              const uchar4 v = src[j];
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+            }
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.y) + (row0 + b) * D);
+            for (int j = lane; j < (D >> 2); j += 32) *reinterpret_cast<float4*>(dst + 4 * j) = src[j];
+          }
+        } else {
+          for (int j = lane; j < D; j += 32) dst[j] = load_y(p, (row0 + b) * D + j);
+        }
+        for (int e = lane; e < Ep; e += 32) {
+          float v = 0.f;
+          if (e < u) v = p.u_in[(row0 + b) * u + e];
+          else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
+          else if (e < E) v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
+          dst[D + e] = v;
+        }
+        if (p.eps) {
+          const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
+          for (int k = lane; k < 2 * d; k += 32) eps_s[b * 2 * d + k] = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d];
+        } else {
+          const int nblk = (d + 3) >> 2;
+          if (lane < 2 * nblk) {
+            const int which = lane / nblk, blk = lane - which * nblk;
+            float z[4];
+            philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
+            for (int k = 0; k < 4; ++k)
+              if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
+          }
+        }
+      } else {
+        // pad rows of everything that is summed over the rows of the tile
+        for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
+        for (int j = lane; j < Rp; j += 32) phi_s[b * Rp + j] = 0.f;
+        for (int j = lane; j < Dp; j += 32) g_s[b * Dp + j] = 0.f;
+        for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; }
+        for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
       }
-    } else {
-      const int nblk = (d + 3) >> 2;
-      for (int i = tid; i < nb * 2 * nblk; i += VJF_NT) {
-        const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
-        float z[4];
-        philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
-        for (int k = 0; k < 4; ++k)
-          if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
-      }
     }
-    // pad rows of everything that is summed over the rows of the tile
-    for (int i = tid; i < (rows - nb) * Rp; i += VJF_NT) phi_s[nb * Rp + i] = 0.f;
-    for (int i = tid; i < (rows - nb) * Dp; i += VJF_NT) g_s[nb * Dp + i] = 0.f;
-    for (int i = tid; i < (rows - nb) * p.Hpmax; i += VJF_NT) { gpa[nb * p.Hpmax + i] = 0.f; gpb[nb * p.Hpmax + i] = 0.f; }
-    for (int i = tid; i < (rows - nb) * d; i += VJF_NT) { dx_s[nb * d + i] = 0.f; gmt_s[nb * d + i] = 0.f; glt_s[nb * d + i] = 0.f; }
   }
   __syncthreads();
 
@@ -176,82 +186,103 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   __syncthreads();
 
   // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
-  for (int i = tid; i < nb * Rp; i += VJF_NT) {
-    const int b = i / Rp, k = i - b * Rp;
-    float v = 0.f;
-    if (k < R) {
-      float d2 = 0.f;
-      for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
-      v = expf(d2 * iw_s[k]);
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    for (int k = lane; k < Rp; k += 32) {
+      float v = 0.f;
+      if (k < R) {
+        float d2 = 0.f;
+        for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
+        v = expf(d2 * iw_s[k]);
+      }
+      phi_s[b * Rp + k] = v;
     }
-    phi_s[b * Rp + k] = v;
   }
   __syncthreads();
 
   // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
   //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
-  for (int b = warp; b < nb; b += VJF_NWARP) {
-    float q = 0.f;
-    for (int k = lane; k < R; k += 32) {
-      float fl = 0.f;
-      const float* ph = phi_s + b * Rp;
-      for (int j = 0; j < R; ++j) fl = fmaf(ph[j], U[j * R + k], fl);
-      q = fmaf(fl, fl, q);
+  if (p.U_in_smem) {
+    mma_quadform(phi_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, u_upper);
+  } else {
+    const float* U = st + p.lay.w_chol;
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      float q = 0.f;
+      for (int k = lane; k < R; k += 32) {
+        float fl = 0.f;
+        const float* ph = phi_s + b * Rp;
+        for (int j = 0; j < R; ++j) fl = fmaf(ph[j], U[j * R + k], fl);
+        q = fmaf(fl, fl, q);
+      }
+      q = warp_sum(q);
+      if (lane == 0) qp_s[b] = q;
     }
-    q = warp_sum(q);
-    if (lane == 0) plv_s[b] = logf(q);
   }
-  for (int i = tid; i < nb * d; i += VJF_NT) {
-    const int b = i / d, k = i - b * d;
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s = fmaf(phi_s[b * Rp + r], W_s[r * d + k], s);
-    pm_s[i] = xu_s[b * du + k] + s;
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    for (int k = 0; k < d; ++k) {
+      float s = 0.f;
+      for (int r = lane; r < R; r += 32) s = fmaf(phi_s[b * Rp + r], W_s[r * d + k], s);
+      s = warp_sum(s);
+      if (lane == 0) pm_s[b * d + k] = xu_s[b * du + k] + s;
+    }
   }
 
-  // ---- S4: recognition MLP (vjf/recognition.py:31-42) ----
+  // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
+  const float* hL; int ldh, HL;
   {
     const float* A = in_s; int lda = K1p, K = K1;
     for (int l = 0; l < L; ++l) {
       float* out = sm + p.s_act[l];
-      tile_linear_fwd(A, lda, K, st + p.lay.mlp_w[l], st + p.lay.mlp_b[l], p.H[l], out, p.Hp[l], rows, true);
-      // zero the pad columns so float4 reads of this activation in the weight-gradient are finite
-      for (int i = tid; i < rows * (p.Hp[l] - p.H[l]); i += VJF_NT) {
-        const int b = i / (p.Hp[l] - p.H[l]), c = i - b * (p.Hp[l] - p.H[l]);
-        out[b * p.Hp[l] + p.H[l] + c] = 0.f;
-      }
+      mma_linear_fwd(A, lda, K, st + p.lay.mlp_w[l], st + p.lay.mlp_b[l], p.H[l], out, p.Hp[l], rows, true);
+      // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
+      const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
+      if (h16 > h8)
+        for (int i = tid; i < rows * (h16 - h8); i += VJF_NT) out[(i / (h16 - h8)) * p.Hp[l] + h8 + i % (h16 - h8)] = 0.f;
       __syncthreads();
       A = out; lda = p.Hp[l]; K = p.H[l];
     }
-    // heads: m_t = W_m h (no bias), l_t = W_v h + b_v ; then xt = m_t + eps2 exp(l_t/2), dx = xt - xs
-    const float* hL = A; const int HL = K, ldh = lda;
-    for (int i = tid; i < nb * d; i += VJF_NT) {
-      const int b = i / d, k = i - b * d;
-      float m = 0.f, lv = st[p.lay.head_v_b + k];
+    hL = A; ldh = lda; HL = K;
+  }
+  // p_logvar from the n-tile partial sums (qp_s complete after the barrier above)
+  if (tid < nb) {
+    float q = qp_s[tid];
+    if (p.U_in_smem) { const int nt = (R + 7) >> 3; for (int n = 1; n < nt; ++n) q += qp_s[n * rows + tid]; }
+    plv_s[tid] = logf(q);
+  }
+  // heads: m_t = W_m h (no bias), l_t = W_v h + b_v ; then xt = m_t + eps2 exp(l_t/2), dx = xt - xs
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    float my_m = 0.f, my_lv = 0.f;
+    for (int k = 0; k < d; ++k) {
+      float m = 0.f, lv = 0.f;
       const float* wm = st + p.lay.head_m_w + k;
       const float* wv = st + p.lay.head_v_w + k;
-      for (int n = 0; n < HL; ++n) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
-      mt_s[i] = m; lt_s[i] = lv;
-      const float x = m + eps_s[b * 2 * d + d + k] * expf(0.5f * lv);
+      for (int n = lane; n < HL; n += 32) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
+      m = warp_sum(m); lv = warp_sum(lv);
+      if (lane == k) { my_m = m; my_lv = lv + st[p.lay.head_v_b + k]; }
+    }
+    if (lane < d) {
+      const int i = b * d + lane;
+      mt_s[i] = my_m; lt_s[i] = my_lv;
+      const float x = my_m + eps_s[b * 2 * d + d + lane] * expf(0.5f * my_lv);
       xt_s[i] = x;
-      const float dxv = x - xu_s[b * du + k];
+      const float dxv = x - xu_s[b * du + lane];
       dx_s[i] = dxv;
       sc[SC_SDX] = fmaf(dxv, dxv, sc[SC_SDX]);
       // posterior of this step -> trajectory (returned by filter / fit, model.py:218-221, :305-307)
-      p.mu[((size_t)t * p.B + b0 + b) * d + k] = m;
-      p.logvar[((size_t)t * p.B + b0 + b) * d + k] = lv;
+      p.mu[((size_t)t * p.B + b0 + b) * d + lane] = my_m;
+      p.logvar[((size_t)t * p.B + b0 + b) * d + lane] = my_lv;
     }
   }
   __syncthreads();
 
   // ---- S5: decoder eta = D xt + bias (model.py:29-30), likelihood terms and dloss/deta (times B) ----
-  {
-    const float* dw = st + p.lay.dec_w;
-    const float* db = st + p.lay.dec_b;
-    for (int i = tid; i < nb * D; i += VJF_NT) {
-      const int b = i / D, j = i - b * D;
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    const float* xtb = xt_s + b * d;
+    const float* yb = in_s + b * K1p;
+    float* gb = g_s + b * Dp;
+    for (int j = lane; j < D; j += 32) {
       float eta = db[j];
-      for (int k = 0; k < d; ++k) eta = fmaf(dw[k * D + j], xt_s[b * d + k], eta);
-      const float yv = in_s[b * K1p + j];
+      for (int k = 0; k < d; ++k) eta = fmaf(dw[k * D + j], xtb[k], eta);
+      const float yv = yb[j];
       float g;
       if (p.lik == VJF_LIK_GAUSSIAN) {
         // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
@@ -272,7 +303,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
         g = (eta <= 10.0f) ? (ex - yv) : 0.f;
         if (eta != eta) { sc[SC_RECON] = eta; g = eta; }  // NaN propagates like torch.clamp
       }
-      g_s[b * Dp + j] = r_on ? g : 0.f;
+      gb[j] = r_on ? g : 0.f;
     }
   }
   __syncthreads();
@@ -282,38 +313,22 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     float* gdw = slot + p.lay.dec_w;
     float* gdb = slot + p.lay.dec_b;
     for (int j = tid; j < D; j += VJF_NT) {
-      float accb = 0.f, acc[VJF_MAX_XDIM];
-#pragma unroll
-      for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
-      for (int b = 0; b < nb; ++b) {
-        const float g = g_s[b * Dp + j];
-        accb += g;
-#pragma unroll
-        for (int k = 0; k < VJF_MAX_XDIM; ++k)
-          if (k < d) acc[k] = fmaf(g, xt_s[b * d + k], acc[k]);
-      }
+      float accb = 0.f;
+      for (int b = 0; b < nb; ++b) accb += g_s[b * Dp + j];
       acc_store(gdb + j, accb, first);
-#pragma unroll
-      for (int k = 0; k < VJF_MAX_XDIM; ++k)
-        if (k < d) acc_store(gdw + k * D + j, acc[k], first);
-    }
-    const float* dw = st + p.lay.dec_w;
-    for (int b = warp; b < nb; b += VJF_NWARP) {
-      float acc[VJF_MAX_XDIM];
-#pragma unroll
-      for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
-      for (int j = lane; j < D; j += 32) {
-        const float g = g_s[b * Dp + j];
-#pragma unroll
-        for (int k = 0; k < VJF_MAX_XDIM; ++k)
-          if (k < d) acc[k] = fmaf(g, dw[k * D + j], acc[k]);
+      for (int k = 0; k < d; ++k) {
+        float acc = 0.f;
+        for (int b = 0; b < nb; ++b) acc = fmaf(g_s[b * Dp + j], xt_s[b * d + k], acc);
+        acc_store(gdw + k * D + j, acc, first);
       }
-#pragma unroll
-      for (int k = 0; k < VJF_MAX_XDIM; ++k)
-        if (k < d) {
-          const float s = warp_sum(acc[k]);
-          if (lane == 0) gxt_s[b * d + k] = s;
-        }
+    }
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      for (int k = 0; k < d; ++k) {
+        float acc = 0.f;
+        for (int j = lane; j < D; j += 32) acc = fmaf(g_s[b * Dp + j], dw[k * D + j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) gxt_s[b * d + k] = acc;
+      }
     }
   }
   __syncthreads();
@@ -339,8 +354,6 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
 
   // ---- S8: backward through the heads and the MLP ----
   {
-    const int HL = p.H[L - 1], ldh = p.Hp[L - 1];
-    const float* hL = sm + p.s_act[L - 1];
     // head weight gradients [H_L][d] (input-major) and logvar-head bias
     for (int i = tid; i < HL * d; i += VJF_NT) {
       const int n = i / d, k = i - n * d;
@@ -349,20 +362,26 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       acc_store(slot + p.lay.head_m_w + i, am, first);
       acc_store(slot + p.lay.head_v_w + i, av, first);
     }
-    for (int k = tid; k < d; k += VJF_NT) {
+    if (tid >= VJF_NT - 32 && lane < d) {
       float s = 0.f;
-      for (int b = 0; b < nb; ++b) s += glt_s[b * d + k];
-      acc_store(slot + p.lay.head_v_b + k, s, first);
+      for (int b = 0; b < nb; ++b) s += glt_s[b * d + lane];
+      acc_store(slot + p.lay.head_v_b + lane, s, first);
     }
-    // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2)
+    // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2); pad columns up to a multiple of 8 are zero
     const float* wm = st + p.lay.head_m_w;
     const float* wv = st + p.lay.head_v_w;
-    for (int i = tid; i < nb * HL; i += VJF_NT) {
-      const int b = i / HL, n = i - b * HL;
-      float s = 0.f;
-      for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], wm[n * d + k], s); s = fmaf(glt_s[b * d + k], wv[n * d + k], s); }
-      const float h = hL[b * ldh + n];
-      gpa[b * p.Hpmax + n] = s * (1.0f - h * h);
+    const int H8 = (HL + 7) & ~7;
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      for (int n = lane; n < H8; n += 32) {
+        float v = 0.f;
+        if (n < HL) {
+          float s = 0.f;
+          for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], wm[n * d + k], s); s = fmaf(glt_s[b * d + k], wv[n * d + k], s); }
+          const float h = hL[b * ldh + n];
+          v = s * (1.0f - h * h);
+        }
+        gpa[b * Gp + n] = v;
+      }
     }
     __syncthreads();
     float* gcur = gpa; float* gnext = gpb;
@@ -370,17 +389,22 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
       const int ldp = (l == 0) ? K1p : p.Hp[l - 1];
       const int Kl = (l == 0) ? K1 : p.H[l - 1];
-      tile_wgrad(Aprev, ldp, Kl, gcur, p.Hpmax, p.H[l], rows, slot + p.lay.mlp_w[l], first);
-      tile_colsum(gcur, p.Hpmax, p.H[l], rows, slot + p.lay.mlp_b[l], first);
+      mma_wgrad(Aprev, ldp, Kl, gcur, Gp, p.H[l], rows, slot + p.lay.mlp_w[l], first);
+      tile_colsum(gcur, Gp, p.H[l], nb, slot + p.lay.mlp_b[l], first);
       if (l > 0) {
         const float* Wl = st + p.lay.mlp_w[l];  // [Kl][H_l]
-        const int N = p.H[l];
-        for (int i = tid; i < nb * Kl; i += VJF_NT) {
-          const int b = i / Kl, k = i - b * Kl;
-          float s = 0.f;
-          for (int n = 0; n < N; ++n) s = fmaf(gcur[b * p.Hpmax + n], Wl[(size_t)k * N + n], s);
-          const float h = Aprev[b * ldp + k];
-          gnext[b * p.Hpmax + k] = s * (1.0f - h * h);
+        const int N = p.H[l], K8 = (Kl + 7) & ~7;
+        for (int b = warp; b < nb; b += VJF_NWARP) {
+          for (int k = lane; k < K8; k += 32) {
+            float v = 0.f;
+            if (k < Kl) {
+              float s = 0.f;
+              for (int n = 0; n < N; ++n) s = fmaf(gcur[b * Gp + n], Wl[k * N + n], s);
+              const float h = Aprev[b * ldp + k];
+              v = s * (1.0f - h * h);
+            }
+            gnext[b * Gp + k] = v;
+          }
         }
         __syncthreads();
         float* tmp = gcur; gcur = gnext; gnext = tmp;
@@ -389,24 +413,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
 
   // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
+  mma_gram(phi_s, Rp, R, rows, slot + p.pa, first);
   {
-    float* Ap = slot + p.pa;
-    const int kb = Rp >> 2;
-    for (int it = tid; it < R * kb; it += VJF_NT) {
-      const int kp = it % R, k0 = (it / R) << 2;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-      for (int b = 0; b < rows; ++b) {
-        const float4 x = *reinterpret_cast<const float4*>(phi_s + b * Rp + k0);
-        const float g = phi_s[b * Rp + kp];
-        a0 = fmaf(x.x, g, a0); a1 = fmaf(x.y, g, a1); a2 = fmaf(x.z, g, a2); a3 = fmaf(x.w, g, a3);
-      }
-      float* o = Ap + (size_t)k0 * R + kp;
-      acc_store(o, a0, first);
-      if (k0 + 1 < R) acc_store(o + R, a1, first);
-      if (k0 + 2 < R) acc_store(o + 2 * R, a2, first);
-      if (k0 + 3 < R) acc_store(o + 3 * R, a3, first);
-    }
     float* bp = slot + p.pb;
     for (int i = tid; i < R * d; i += VJF_NT) {
       const int r = i / d, k = i - r * d;
@@ -432,26 +440,41 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   __syncthreads();
 }
 
-// Load the parameters every tile of this step shares into shared memory.
-static __device__ void phase_a_prologue(const StepParams& p, float* sm) {
+// Load the parameters every tile of this step shares into shared memory.  Returns (block-uniform) whether
+// w_chol is upper triangular, which lets the quadratic form skip the zero blocks.
+static __device__ int phase_a_prologue(const StepParams& p, float* sm) {
   const int tid = threadIdx.x;
   const float* st = p.state;
   float* W_s = sm + p.s_W; float* c_s = sm + p.s_c; float* iw_s = sm + p.s_iw;
   for (int i = tid; i < p.R * p.d; i += VJF_NT) W_s[i] = st[p.lay.w_mean + i];
   for (int i = tid; i < p.R * p.du; i += VJF_NT) c_s[i] = st[p.lay.centroid + i];
   for (int i = tid; i < p.R; i += VJF_NT) { const float w = expf(st[p.lay.logwidth + i]); iw_s[i] = -0.5f / (w * w); }
+  if (p.dec_in_smem) {
+    float* dec = sm + p.s_dec;
+    for (int i = tid; i < p.d * p.D; i += VJF_NT) dec[i] = st[p.lay.dec_w + i];
+    for (int i = tid; i < p.D; i += VJF_NT) dec[p.d * p.D + i] = st[p.lay.dec_b + i];
+  }
+  int lower_nonzero = 0;
   if (p.U_in_smem) {
     float* U_s = sm + p.s_U;
-    for (int i = tid; i < p.R * p.R; i += VJF_NT) U_s[i] = st[p.lay.w_chol + i];
+    const int Rk = (p.R + 7) & ~7, ldu = p.ldu;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < Rk; r += VJF_NWARP) {
+      for (int c = lane; c < ldu; c += 32) {
+        float v = 0.f;
+        if (r < p.R && c < p.R) { v = st[p.lay.w_chol + r * p.R + c]; if (c < r && v != 0.f) lower_nonzero = 1; }
+        U_s[r * ldu + c] = v;
+      }
+    }
   }
-  __syncthreads();
+  return !__syncthreads_or(lower_nonzero);
 }
 
 static __device__ void phase_a(const StepParams& p, float* sm, int t, unsigned masks) {
-  phase_a_prologue(p, sm);
+  const int u_upper = phase_a_prologue(p, sm);
   bool first = true;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    phase_a_tile(p, sm, t, tile, first, masks);
+    phase_a_tile(p, sm, t, tile, first, masks, u_upper);
     first = false;
   }
   if (first) {  // a CTA without tiles still owns a slot: zero it
@@ -544,10 +567,257 @@ static __device__ double block_sum_d(double v, double* red) {
   return s;
 }
 
+// ---- LinearRegression.rls (vjf/module.py:89-102), register-resident ------------------------------------
+// Work matrix rows: [0,R) lower triangle of P' = P + A/v ; [R,R+d) g^T with g = P W + b/v ; [R+d,2R+d) I.
+// A right-looking LDL^T sweep over the R columns of P' applies the same eliminations to the appended
+// rows, i.e. performs the forward substitutions L^-1 g and L^-1 I on the fly; after scaling column k by
+// 1/sqrt(pivot_k) the three row groups hold chol(P'), (L^-1 g)^T and L^-T = w_chol.  Row r lives in warp
+// r % 16 (register slot r / 16), column j in lane j % 32 (slot j / 32): the sweep touches shared memory only
+// to broadcast the current column.  Returns false (block-uniform) if a pivot is not positive.
+template <int CPL, int RPW>
+static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = p.R, d = p.d, NR = 2 * R + d;
+  const int NRp = (NR + 3) & ~3;
+  float* colbuf = sm;                           // [2][NRp]
+  float* dvec = colbuf + 2 * NRp;               // [R]
+  float* zbuf = dvec + ((R + 3) & ~3);          // [d][R]   g, later z = L^-1 g
+  float* wbuf = zbuf + ((d * R + 3) & ~3);      // [R][d]   W'
+  float* misc = wbuf + ((d * R + 3) & ~3);      // [0..1] 1/pivot (double buffered), [2] fail flag
+  float* st = p.state;
+  const float* P = st + p.lay.w_precision;
+  const float* W = st + p.lay.w_mean;
+  float v[RPW][CPL];
+  float v0[(RPW + 1) / 2][CPL];                 // P' rows kept for the commit (P rows occupy the first slots)
+  if (tid == 0) misc[2] = 0.f;
+#pragma unroll
+  for (int ri = 0; ri < RPW; ++ri) {
+    const int r = warp + VJF_NWARP * ri;
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = 0.f;
+    if (r < R) {
+#pragma unroll
+      for (int ci = 0; ci < CPL; ++ci) {
+        const int j = lane + 32 * ci;
+        v[ri][ci] = (j < R) ? P[r * R + j] : 0.f;
+      }
+      // g[r][c] = sum_j P[r][j] W[j][c] + b[r][c]/v   (old P, old W: module.py:93)
+      for (int c = 0; c < d; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CPL; ++ci) {
+          const int j = lane + 32 * ci;
+          if (j < R) s = fmaf(v[ri][ci], W[j * d + c], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) zbuf[c * R + r] = fmaf(bv[r * d + c], iv, s);
+      }
+#pragma unroll
+      for (int ci = 0; ci < CPL; ++ci) {
+        const int j = lane + 32 * ci;
+        if (j <= r) v[ri][ci] = fmaf(A[r * R + j], iv, v[ri][ci]);  // lower triangle of the symmetric A
+        if (ri < (RPW + 1) / 2) v0[ri][ci] = v[ri][ci];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ri = 0; ri < RPW; ++ri) {
+    const int r = warp + VJF_NWARP * ri;
+    if (r >= R && r < NR) {
+#pragma unroll
+      for (int ci = 0; ci < CPL; ++ci) {
+        const int j = lane + 32 * ci;
+        if (r < R + d) v[ri][ci] = (j < R) ? zbuf[(r - R) * R + j] : 0.f;
+        else v[ri][ci] = (j == r - R - d) ? 1.0f : 0.f;
+      }
+    }
+  }
+  // publish column 0 and 1/pivot_0
+  {
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int r = warp + VJF_NWARP * ri;
+      if (lane == 0 && r < NR) colbuf[r] = v[ri][0];
+    }
+    if (warp == 0 && lane == 0) { const float pv = v[0][0]; misc[0] = 1.0f / pv; if (!(pv > 0.f)) misc[2] = 1.f; }
+  }
+  __syncthreads();
+  int kb = 0;
+  bool fail = false;
+  for (int k = 0; k < R; ++k) {
+    const float* cb = colbuf + kb * NRp;
+    if (misc[2] != 0.f) { fail = true; break; }
+    const float inv = misc[kb];
+    if (tid == 0) dvec[k] = cb[k];
+    float cj[CPL];
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) { const int j = lane + 32 * ci; cj[ci] = (j > k && j < R) ? cb[j] : 0.f; }
+    const int kn = k + 1, ln = kn & 31, cn = kn >> 5;
+    float* cbn = colbuf + (kb ^ 1) * NRp;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+      const int r = warp + VJF_NWARP * ri;
+      // active rows: below the pivot row; identity row c only once column c has been reached
+      const bool active = (r > k) && (r < NR) && !(r >= R + d && r - R - d > k);
+      if (active) {
+        const float tk = cb[r] * inv;
+#pragma unroll
+        for (int ci = 0; ci < CPL; ++ci) {
+          const int j = lane + 32 * ci;
+          if (r >= R || j <= r) v[ri][ci] = fmaf(-tk, cj[ci], v[ri][ci]);
+        }
+      }
+      if (kn < R && lane == ln && r < NR) {
+        float x = v[ri][0];
+#pragma unroll
+        for (int ci = 1; ci < CPL; ++ci) x = (cn == ci) ? v[ri][ci] : x;
+        cbn[r] = x;
+        if (r == kn) { misc[kb ^ 1] = 1.0f / x; if (!(x > 0.f)) misc[2] = 1.f; }
+      }
+    }
+    __syncthreads();
+    kb ^= 1;
+  }
+  if (!fail && misc[2] != 0.f) fail = true;
+  if (fail) return false;
+  __syncthreads();
+  // ---- scale the columns and commit: w_pchol = L, w_chol = L^-T, z ; then W' = w_chol z ----
+  float* Lout = st + p.lay.w_pchol;
+  float* Uout = st + p.lay.w_chol;
+  float* Pout = st + p.lay.w_precision;
+  float sdv[CPL];
+#pragma unroll
+  for (int ci = 0; ci < CPL; ++ci) {
+    const int j = lane + 32 * ci;
+    sdv[ci] = (j < R) ? sqrtf(dvec[j]) : 1.f;
+  }
+#pragma unroll
+  for (int ri = 0; ri < RPW; ++ri) {
+    const int r = warp + VJF_NWARP * ri;
+    if (r >= NR) continue;
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      if (j >= R) continue;
+      const float x = v[ri][ci] / sdv[ci];
+      if (r < R) {
+        Lout[r * R + j] = (j < r) ? x : ((j == r) ? sdv[ci] : 0.f);
+        if (ri < (RPW + 1) / 2 && j <= r) { Pout[r * R + j] = v0[ri][ci]; Pout[j * R + r] = v0[ri][ci]; }
+      } else if (r < R + d) {
+        zbuf[(r - R) * R + j] = x;
+      } else {
+        const int c = r - R - d;
+        const float uv = (j >= c) ? x : 0.f;
+        Uout[c * R + j] = uv;
+        v[ri][ci] = uv;
+      }
+    }
+  }
+  __syncthreads();
+  float* Wout = st + p.lay.w_mean;
+#pragma unroll
+  for (int ri = 0; ri < RPW; ++ri) {
+    const int r = warp + VJF_NWARP * ri;
+    if (r >= R + d && r < NR) {
+      const int c = r - R - d;
+      for (int i = 0; i < d; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CPL; ++ci) {
+          const int j = lane + 32 * ci;
+          if (j < R) s = fmaf(v[ri][ci], zbuf[i * R + j], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) Wout[c * d + i] = s;
+      }
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// Fallback for n_rbf > 128: the same sweep with the work matrix in shared memory.
+static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv, const float* A, const float* bv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = p.R, d = p.d, ldm = p.ldm;
+  float* st = p.state;
+  const float* P = st + p.lay.w_precision;
+  const float* Wold = st + p.lay.w_mean;
+  float* M = sm;                                   // [(2R+d)][ldm]
+  float* dvec = sm + (size_t)(2 * R + d) * ldm;    // [R] pivots
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    if (c <= r) M[r * ldm + c] = fmaf(A[i], iv, P[i]);
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int k = i / d, c = i - k * d;
+    float s = 0.f;
+    for (int j = 0; j < R; ++j) s = fmaf(P[k * R + j], Wold[j * d + c], s);
+    M[(R + c) * ldm + k] = fmaf(bv[i], iv, s);
+  }
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    M[(R + d + r) * ldm + c] = (r == c) ? 1.0f : 0.f;
+  }
+  __syncthreads();
+  float piv = M[0];
+  float inv = 1.0f / piv;
+  bool fail = !(piv > 0.f);
+  for (int k = 0; k < R && !fail; ++k) {
+    if (tid == 0) dvec[k] = piv;
+    float pivn = 1.f;
+    if (k + 1 < R) {
+      const float l = M[(k + 1) * ldm + k];
+      pivn = fmaf(-(l * inv), l, M[(k + 1) * ldm + k + 1]);
+    }
+    const int rend = R + d + k + 1;
+    for (int r = k + 1 + warp; r < rend; r += VJF_NWARP) {
+      const float tk = M[r * ldm + k] * inv;
+      const int jend = (r < R) ? (r + 1) : R;
+      for (int j = k + 1 + lane; j < jend; j += 32) {
+        if (r == k + 1 && j == k + 1) continue;  // next pivot lives in registers
+        M[r * ldm + j] = fmaf(-tk, M[j * ldm + k], M[r * ldm + j]);
+      }
+    }
+    if (k + 1 < R && !(pivn > 0.f)) fail = true;
+    piv = pivn;
+    inv = 1.0f / pivn;
+    __syncthreads();
+  }
+  if (fail) return false;
+  __syncthreads();
+  float* Lout = st + p.lay.w_pchol;
+  float* Uout = st + p.lay.w_chol;
+  float* Pout = st + p.lay.w_precision;
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    const float sd = sqrtf(dvec[c]);
+    Lout[i] = (c < r) ? M[r * ldm + c] / sd : ((c == r) ? sd : 0.f);
+    Uout[i] = (c >= r) ? M[(R + d + r) * ldm + c] / sd : 0.f;
+    const int lo = (c <= r) ? i : (c * R + r);
+    Pout[i] = fmaf(A[lo], iv, P[lo]);
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int k = i / d, c = i - k * d;
+    M[(R + c) * ldm + k] = M[(R + c) * ldm + k] / sqrtf(dvec[k]);
+  }
+  __syncthreads();
+  float* Wout = st + p.lay.w_mean;
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int r = i / d, c = i - r * d;
+    float s = 0.f;
+    for (int k = r; k < R; ++k) s = fmaf(Uout[r * R + k], M[(R + c) * ldm + k], s);
+    Wout[i] = s;
+  }
+  __syncthreads();
+  return true;
+}
+
 // finmask: bit0 recon finite, bit1 dyn finite, bit2 entropy finite (from the reduced sums)
 static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned finmask) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int R = p.R, d = p.d, ldm = p.ldm;
+  const int R = p.R, d = p.d;
   float* st = p.state;
   const float* red = p.reduced;
   const float* A = red + p.pa;
@@ -556,10 +826,6 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   const float Bf = (float)p.Bglobal;
   const bool warm = p.flags & VJF_FLAG_WARMUP;
   const bool upd = p.flags & VJF_FLAG_UPDATE;
-  float* M = sm;                                   // [(2R+d)][ldm]
-  float* dvec = sm + (size_t)(2 * R + d) * ldm;    // [R] pivots
-  const size_t doff = ((size_t)(2 * R + d) * ldm + ((R + 3) & ~3) + 5) & ~(size_t)1;  // 8-byte aligned
-  double* dred = reinterpret_cast<double*>(sm + doff);                          // [NWARP]
 
   if (tid == 0 && !p.init_mode) {
     unsigned stbits = 0;
@@ -589,98 +855,33 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   // rls(x, target, v): v = exp(state logvar) in a filter step (model.py:371); in initialize v is the
   // mean squared increment (model.py:384-385)
   const float iv = p.init_mode ? (Bf * (float)d) / scal[SC_SDX] : 1.0f / expf(gam);
-  const float* P = st + p.lay.w_precision;
-  const float* Wold = st + p.lay.w_mean;
-
+  __syncthreads();
   if (!warm) {
-    // ---- LinearRegression.rls (vjf/module.py:89-102) ----
-    // M rows [0,R): lower triangle of P' = P + A/v ; rows [R,R+d): g^T, g = P W + b/v ; rows [R+d,2R+d): I
-    for (int i = tid; i < R * R; i += VJF_NT) {
-      const int r = i / R, c = i - r * R;
-      if (c <= r) M[r * ldm + c] = fmaf(A[i], iv, P[i]);
-    }
-    for (int i = tid; i < R * d; i += VJF_NT) {
-      const int k = i / d, c = i - k * d;
-      float s = 0.f;
-      for (int j = 0; j < R; ++j) s = fmaf(P[k * R + j], Wold[j * d + c], s);
-      M[(R + c) * ldm + k] = fmaf(bv[i], iv, s);
-    }
-    for (int i = tid; i < R * R; i += VJF_NT) {
-      const int r = i / R, c = i - r * R;
-      M[(R + d + r) * ldm + c] = (r == c) ? 1.0f : 0.f;
-    }
+    bool ok;
+    if (R <= 64) ok = rls_factor_regs<2, 9>(p, sm, iv, A, bv);
+    else if (R <= 128) ok = rls_factor_regs<4, 17>(p, sm, iv, A, bv);
+    else ok = rls_factor_smem(p, sm, iv, A, bv);
+    if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
-    // right-looking LDL^T sweep; appended rows receive the same eliminations, i.e. the forward substitutions
-    float piv = M[0];
-    float inv = 1.0f / piv;
-    bool fail = !(piv > 0.f);
-    for (int k = 0; k < R && !fail; ++k) {
-      if (tid == 0) dvec[k] = piv;
-      float pivn = 1.f;
-      if (k + 1 < R) {
-        const float l = M[(k + 1) * ldm + k];
-        pivn = fmaf(-(l * inv), l, M[(k + 1) * ldm + k + 1]);
-      }
-      const int rend = R + d + k + 1;
-      for (int r = k + 1 + warp; r < rend; r += VJF_NWARP) {
-        const float tk = M[r * ldm + k] * inv;
-        const int jend = (r < R) ? (r + 1) : R;
-        for (int j = k + 1 + lane; j < jend; j += 32) {
-          if (r == k + 1 && j == k + 1) continue;  // next pivot lives in registers
-          M[r * ldm + j] = fmaf(-tk, M[j * ldm + k], M[r * ldm + j]);
-        }
-      }
-      if (k + 1 < R && !(pivn > 0.f)) fail = true;
-      piv = pivn;
-      inv = 1.0f / pivn;
-      __syncthreads();
-    }
-    if (fail) {
-      if (tid == 0) { atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED); }
-    } else {
-      __syncthreads();
-      // scale: L = M D^-1/2 ; z = (L^-1 g)^T ; U = L^-T  (all columns k scaled by 1/sqrt(piv_k))
-      float* Lout = st + p.lay.w_pchol;
-      float* Uout = st + p.lay.w_chol;
-      float* Pout = st + p.lay.w_precision;
-      for (int i = tid; i < R * R; i += VJF_NT) {
-        const int r = i / R, c = i - r * R;
-        const float sd = sqrtf(dvec[c]);
-        Lout[i] = (c < r) ? M[r * ldm + c] / sd : ((c == r) ? sd : 0.f);
-        const float uv = (c >= r) ? M[(R + d + r) * ldm + c] / sd : 0.f;
-        Uout[i] = uv;
-        Pout[i] = fmaf(A[i], iv, P[i]);
-      }
-      for (int i = tid; i < R * d; i += VJF_NT) {
-        const int k = i / d, c = i - k * d;
-        M[(R + c) * ldm + k] = M[(R + c) * ldm + k] / sqrtf(dvec[k]);
-      }
-      __syncthreads();
-      // W' = U z : W'[r][c] = sum_{k>=r} U[r][k] z[c][k]
-      float* Wout = st + p.lay.w_mean;
-      for (int i = tid; i < R * d; i += VJF_NT) {
-        const int r = i / d, c = i - r * d;
-        float s = 0.f;
-        for (int k = r; k < R; ++k) s = fmaf(Uout[r * R + k], M[(R + c) * ldm + k], s);
-        Wout[i] = s;
-      }
-      __syncthreads();
-    }
   }
-  (void)lane;
 
   // ---- state-noise running variance (vjf/model.py:373-377).  sum |dx - phi W'|^2 from the reduced
   //      statistics: S - 2 <W', b> + <W', A W'>, evaluated in double ----
   {
-    const float* Wn = st + p.lay.w_mean;
+    float* wbuf = sm;                                      // [R][d] current W
+    const size_t doff = ((size_t)R * d + 5) & ~(size_t)1;  // 8-byte aligned
+    double* dred = reinterpret_cast<double*>(sm + doff);   // [NWARP]
+    for (int i = tid; i < R * d; i += VJF_NT) wbuf[i] = st[p.lay.w_mean + i];
+    __syncthreads();
     double acc = 0.0;
-    for (int i = tid; i < R * R; i += VJF_NT) {
-      const int r = i / R, c = i - r * R;
-      double w2 = 0.0;
-      for (int k = 0; k < d; ++k) w2 += (double)Wn[r * d + k] * (double)Wn[c * d + k];
-      acc += (double)A[i] * w2;
+    for (int r = warp; r < R; r += VJF_NWARP) {
+      for (int j = lane; j <= r; j += 32) {  // lower triangle of the symmetric A, off-diagonal counted twice
+        double w2 = 0.0;
+        for (int k = 0; k < d; ++k) w2 += (double)wbuf[r * d + k] * (double)wbuf[j * d + k];
+        acc += (j < r ? 2.0 : 1.0) * (double)A[r * R + j] * w2;
+      }
     }
-    for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)Wn[i] * (double)bv[i];
+    for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)wbuf[i] * (double)bv[i];
     const double tot = block_sum_d(acc, dred) + (double)scal[SC_SDX];
     if (tid == 0) {
       const float mse = (float)(fmax(tot, 0.0) / ((double)p.Bglobal * (double)d));
