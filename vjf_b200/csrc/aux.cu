@@ -15,7 +15,10 @@ vjf_rls_stats_kernel(const __grid_constant__ StepParams p, const float* xs, cons
   const int d = p.d, u = p.u, du = p.du, R = p.R, Rp = p.Rp;
   float* phi_s = sm + p.s_phi; float* xu_s = sm + p.s_xu; float* dx_s = sm + p.s_dx;
   float* c_s = sm + p.s_c; float* iw_s = sm + p.s_iw; float* red_s = sm + p.s_red;
-  phase_a_prologue(p, sm);
+  // shared parameters of the RBF features
+  for (int i = tid; i < p.R * p.du; i += VJF_NT) c_s[i] = p.state[p.lay.centroid + i];
+  for (int i = tid; i < p.R; i += VJF_NT) { const float w = expf(p.state[p.lay.logwidth + i]); iw_s[i] = -0.5f / (w * w); }
+  __syncthreads();
   float* slot = p.partials + (size_t)blockIdx.x * p.PS;
   const int TB = VJF_TB_MAX;
   const long long ntiles = (N + TB - 1) / TB;
@@ -112,7 +115,7 @@ extern "C" int vjf_rls_initialize(vjf_handle* h, int64_t N, const float* xs, con
     p.s_c = take((size_t)p.R * p.du);
     p.s_iw = take((size_t)p.R);
     p.s_red = take(VJF_NWARP * VJF_NSCAL + 64);
-    size_t b2 = 2 * (size_t)(2 * p.R + p.d + 4) + p.R + 4 + 2 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
+    size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
     if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
     p.s_total = (int)std::max(std::max(off, b2), (size_t)1024);
     if ((size_t)p.s_total * 4 > h->smem_limit) { vjf_set_error("n_rbf=%d too large for this build", p.R); return -1; }

@@ -37,8 +37,8 @@ struct StepParams {
   int TB, ntiles, nslots;
   // ---- shared-memory plan (float offsets) ----
   int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
-      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_total;
-  int U_in_smem, dec_in_smem;
+      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_total;
+  int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
   float* state;
@@ -61,6 +61,7 @@ struct StepParams {
   float lr;
   int T;
   int red_begin;   // first element of the partial vector the reduction touches
+  long long* dbg;  // optional [T][8] per-phase globaltimer stamps of CTA 0 (development aid)
   int init_mode;   // phase B2 runs as RBFDS.initialize (vjf/model.py:379-388) instead of a filter step
 };
 
@@ -133,6 +134,39 @@ __device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned
   sincosf(TWO_PI * u3, &s1, &c1);
   out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
 }
+
+// ---- Ampere-style async global->shared copies (LDGSTS): no register staging, overlap with compute ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage a [rows][cols] global matrix (row stride lds) into shared memory with row stride ldd
+__device__ __forceinline__ void stage_async(float* dst, int ldd, const float* src, int lds, int rows, int cols, int tid, int nthr) {
+  if (((cols | lds | ldd) & 3) == 0 && ((((size_t)src) | ((size_t)dst)) & 15) == 0) {
+    const int c4 = cols >> 2;
+    for (int i = tid; i < rows * c4; i += nthr) { const int r = i / c4, c = (i - r * c4) << 2; cp_async16(dst + r * ldd + c, src + r * lds + c); }
+  } else {
+    for (int i = tid; i < rows * cols; i += nthr) { const int r = i / cols, c = i - r * cols; cp_async4(dst + r * ldd + c, src + r * lds + c); }
+  }
+}
+
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// development aid: CTA 0 / thread 0 drops a globaltimer stamp into slot idx of step t (64 slots per step)
+#define VJF_STAMP(p, t, idx)                                                              \
+  do {                                                                                    \
+    if ((p).dbg && blockIdx.x == 0 && threadIdx.x == 0) (p).dbg[(t) * 64 + (idx)] = gtime_ns(); \
+  } while (0)
 
 // clamp that propagates NaN the way torch.clamp does (fminf/fmaxf would drop it)
 __device__ __forceinline__ float clip1(float g) { return g < -1.0f ? -1.0f : (g > 1.0f ? 1.0f : g); }

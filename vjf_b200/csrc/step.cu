@@ -36,9 +36,12 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
   unsigned target = 0;
   for (int t = 0; t < p.T; ++t) {
     unsigned masks = base_masks(p), fin;
+    VJF_STAMP(p, t, 0);
     for (int attempt = 0;; ++attempt) {
       phase_a(p, sm, t, masks);
+      VJF_STAMP(p, t, 1);
       grid_barrier(p.barrier, target);
+      VJF_STAMP(p, t, 2);
       fin = term_finite_mask(p, p.partials, gridDim.x, sm);
       // vjf/model.py:138-145: a non-finite term becomes the constant 0 => it must not contribute a
       // gradient either.  Rare; redo the trial-parallel phase with that term switched off.
@@ -51,9 +54,13 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       break;
     }
     phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x);
+    VJF_STAMP(p, t, 3);
     grid_barrier(p.barrier, target);
+    VJF_STAMP(p, t, 4);
     if (blockIdx.x == 0) phase_b2(p, sm, t, fin);
+    VJF_STAMP(p, t, 5);
     grid_barrier(p.barrier, target);
+    VJF_STAMP(p, t, 6);
   }
 }
 
@@ -148,12 +155,12 @@ static int pad_mod32(int lo, int tgt) {
 
 // shared-memory plan for a tile of `tb` trials (rows padded to a multiple of 16 for the MMA tiles);
 // returns the number of floats (maximum over phase A, B1 and B2)
-static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem) {
+static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem, bool w1_in_smem) {
   const int rows = (tb + 15) & ~15;
   size_t off = 0;
   auto take = [&](size_t n) { size_t at = off; off = (off + n + 3) & ~(size_t)3; return (int)at; };
   p.s_in = take((size_t)rows * p.K1p);
-  p.s_g = take((size_t)rows * p.Dp);
+  p.s_g = take((size_t)((tb + 3) & ~3) * p.Dp);  // only real trials are read back
   p.s_phi = take((size_t)rows * p.Rp);
   for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)rows * p.Hp[l]);
   p.s_gpa = take((size_t)rows * p.Gp);
@@ -168,6 +175,11 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem)
   p.s_U = take(u_in_smem ? (size_t)((p.R + 7) & ~7) * p.ldu : 0);
   p.dec_in_smem = dec_in_smem ? 1 : 0;
   p.s_dec = take(dec_in_smem ? (size_t)(p.d + 1) * p.D : 0);
+  p.W1_in_smem = w1_in_smem ? 1 : 0;
+  p.s_W1 = take(w1_in_smem ? (size_t)p.K1 * p.ldw1 : 0);
+  p.s_hm = take((size_t)p.H[p.L - 1] * p.d);
+  p.s_hv = take((size_t)p.H[p.L - 1] * p.d + p.d);
+  p.s_flag = take(4);
   p.s_W = take((size_t)p.R * p.d);
   p.s_c = take((size_t)p.R * p.du);
   p.s_iw = take((size_t)p.R);
@@ -175,7 +187,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem)
   const size_t a = off;
   // phase B2: register path needs ~2(2R+d) + R + 2dR floats; the shared-memory fallback (R > 128)
   // [(2R+d)][ldm] + pivots; phase B1: 512 floats
-  size_t b2 = 2 * (size_t)(2 * p.R + p.d + 4) + p.R + 4 + 2 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
+  size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
   if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
   p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
   return (size_t)p.s_total;
@@ -187,10 +199,13 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots) {
   const size_t limit = h->smem_limit;
   bool u_smem = (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
   bool dec_smem = (size_t)(p.d + 1) * p.D * 4 <= 32 * 1024;
+  bool w1_smem = (size_t)p.K1 * p.ldw1 * 4 <= 72 * 1024;
   int tb = want;
   for (;;) {
-    if (plan_smem(p, tb, u_smem, dec_smem) * 4 <= limit) break;
+    if (plan_smem(p, tb, u_smem, dec_smem, w1_smem) * 4 <= limit) break;
+    if (w1_smem && tb <= want - 8) { w1_smem = false; tb = want; continue; }
     if (tb > 4) { tb -= 4; continue; }
+    if (w1_smem) { w1_smem = false; tb = want; continue; }
     if (dec_smem) { dec_smem = false; tb = want; continue; }
     if (u_smem) { u_smem = false; tb = want; continue; }
     vjf_set_error("configuration does not fit in %zu bytes of shared memory (ydim=%d n_rbf=%d)", limit, p.D, p.R);
@@ -249,6 +264,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
     hmax = std::max(hmax, p.H[l]);
   }
   p.Gp = pad_mod32((int)up(hmax, 8), 8);
+  p.ldw1 = pad_mod32((int)up(p.H[0], 4), 8);
   p.lik = cfg->likelihood;
   lay_to_int(lay, p.lay);
   p.G = p.lay.n_train;
@@ -333,6 +349,10 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
   return 0;
 }
 
+// development aid (not part of the public header): per-phase timestamps of CTA 0 for the next launches
+static long long* g_dbg_ptr = nullptr;
+extern "C" void vjf_debug_set_stamps(long long* dev_ptr) { g_dbg_ptr = dev_ptr; }
+
 extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32_t y_dtype, const float* u,
                        const float* q0_mean, const float* q0_logvar, const float* eps, uint64_t seed, uint64_t step0,
                        uint32_t flags, float lr, float* mu, float* logvar, float* losses, void* stream) {
@@ -345,6 +365,7 @@ extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32
   p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
   p.mu = mu; p.logvar = logvar; p.losses = losses;
   p.seed = seed; p.step0 = step0; p.trial_offset = 0; p.flags = flags; p.lr = lr; p.T = T;
+  p.dbg = g_dbg_ptr;
   return launch_persistent(h, p, (cudaStream_t)stream);
 }
 

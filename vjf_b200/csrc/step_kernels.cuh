@@ -50,7 +50,12 @@ __device__ __forceinline__ void tile_linear_fwd(const float* A, int lda, int K, 
   }
 }
 
-__device__ __forceinline__ void acc_store(float* p, float v, bool first) { *p = first ? v : (*p + v); }
+// A CTA's slot is written by that CTA only: the first tile stores, later tiles add with a fire-and-forget
+// reduction (same thread, same address => program order, so the sum order stays deterministic).
+__device__ __forceinline__ void acc_store(float* p, float v, bool first) {
+  if (first) *p = v;
+  else atomicAdd(p, v);
+}
 
 // dW[k][n] (+)= sum_b A[b][k] G[b][n]      A, G: smem; dW: this CTA's slot (global) [K][N]
 __device__ __forceinline__ void tile_wgrad(const float* A, int lda, int K, const float* G, int ldg, int N, int rows,
@@ -93,8 +98,80 @@ __device__ __forceinline__ float load_y(const StepParams& p, size_t idx) {
                                : reinterpret_cast<const float*>(p.y)[idx];
 }
 
+// Decoder + likelihood + their gradients for one tile; DX >= d is the compile-time bound of the state loops.
+template <int DX>
+static __device__ __forceinline__ void decoder_stage(const StepParams& p, float* sm, int nb, bool first, bool r_on, float lam,
+                                                     float p_lam, float e_nlam, const float* dw, const float* db, float* slot,
+                                                     float* sc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = p.D, d = p.d, K1p = p.K1p, Dp = p.Dp;
+  const float* in_s = sm + p.s_in; float* g_s = sm + p.s_g; const float* xt_s = sm + p.s_xt; float* gxt_s = sm + p.s_gxt;
+  for (int b = warp; b < nb; b += VJF_NWARP) {
+    float xt[DX], gx[DX];
+#pragma unroll
+    for (int k = 0; k < DX; ++k) { xt[k] = (k < d) ? xt_s[b * d + k] : 0.f; gx[k] = 0.f; }
+    const float* yb = in_s + b * K1p;
+    float* gb = g_s + b * Dp;
+    for (int j = lane; j < D; j += 32) {
+      float w[DX];
+      float eta = db[j];
+#pragma unroll
+      for (int k = 0; k < DX; ++k) { w[k] = (DX == d || k < d) ? dw[k * D + j] : 0.f; eta = fmaf(w[k], xt[k], eta); }
+      const float yv = yb[j];
+      float g;
+      if (p.lik == VJF_LIK_GAUSSIAN) {
+        // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
+        const float r = yv - eta;
+        const float rs = yv * p_lam - eta * p_lam;
+        const float mse = rs * rs;
+        if (!isfinite(mse)) sc[SC_BADMSE] += 1.f;
+        sc[SC_RECON] += 0.5f * (mse + lam);
+        sc[SC_SSE] = fmaf(r, r, sc[SC_SSE]);
+        g = -r * e_nlam;
+        // d/dlambda = 0.5 (1 - r^2 e^-lambda) ; accumulated into the lik_logvar gradient slot
+        sc[6] += r_on ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
+      } else {
+        // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62
+        const float ec = fminf(eta, 10.0f);
+        const float ex = expf(ec);
+        sc[SC_RECON] += ex - yv * ec;
+        g = (eta <= 10.0f) ? (ex - yv) : 0.f;
+        if (eta != eta) { sc[SC_RECON] = eta; g = eta; }  // NaN propagates like torch.clamp
+      }
+      g = r_on ? g : 0.f;
+      gb[j] = g;
+#pragma unroll
+      for (int k = 0; k < DX; ++k) gx[k] = fmaf(g, w[k], gx[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < DX; ++k) {
+      const float s = warp_sum(gx[k]);
+      if (lane == 0 && k < d) gxt_s[b * d + k] = s;
+    }
+  }
+  __syncthreads();
+  float* gdw = slot + p.lay.dec_w;
+  float* gdb = slot + p.lay.dec_b;
+  for (int j = tid; j < D; j += VJF_NT) {
+    float accb = 0.f, acc[DX];
+#pragma unroll
+    for (int k = 0; k < DX; ++k) acc[k] = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const float g = g_s[b * Dp + j];
+      accb += g;
+#pragma unroll
+      for (int k = 0; k < DX; ++k)
+        if (DX == d || k < d) acc[k] = fmaf(g, xt_s[b * d + k], acc[k]);
+    }
+    acc_store(gdb + j, accb, first);
+#pragma unroll
+    for (int k = 0; k < DX; ++k)
+      if (k < d) acc_store(gdw + k * D + j, acc[k], first);
+  }
+}
+
 // masks: bit0 recon term on, bit1 dynamics term on (already combined with !warm_up), bit2 entropy term on
-static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int u_upper) {
+static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
   const int K1 = p.K1, K1p = p.K1p, Dp = p.Dp, Rp = p.Rp, Gp = p.Gp;
@@ -108,6 +185,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   float* gxt_s = sm + p.s_gxt; float* gmt_s = sm + p.s_gmt; float* glt_s = sm + p.s_glt;
   float* plv_s = sm + p.s_plv; float* W_s = sm + p.s_W;     float* c_s = sm + p.s_c;
   float* iw_s = sm + p.s_iw;   float* red_s = sm + p.s_red; float* qp_s = sm + p.s_qp;
+  const float* hm_s = sm + p.s_hm; const float* hv_s = sm + p.s_hv;  // head weights [H_L][d], then head_v_b at hv_s[H_L*d]
+  int* flag_s = reinterpret_cast<int*>(sm + p.s_flag);
   float* st = p.state;
   const float* dw = p.dec_in_smem ? (sm + p.s_dec) : (st + p.lay.dec_w);        // [d][D]
   const float* db = p.dec_in_smem ? (sm + p.s_dec + d * D) : (st + p.lay.dec_b);  // [D]
@@ -167,14 +246,28 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
         // pad rows of everything that is summed over the rows of the tile
         for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
         for (int j = lane; j < Rp; j += 32) phi_s[b * Rp + j] = 0.f;
-        for (int j = lane; j < Dp; j += 32) g_s[b * Dp + j] = 0.f;
         for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; }
         for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
       }
     }
   }
+  VJF_STAMP(p, t, 22);
+  cp_async_wait_all();  // shared parameters staged by phase_a_prologue (no-op after the first tile)
+  VJF_STAMP(p, t, 23);
   __syncthreads();
 
+  VJF_STAMP(p, t, 8);
+  if (first) {
+    // finish the staged parameters: 1/w^2 scaling of the RBF widths, and whether w_chol is upper triangular
+    for (int i = tid; i < R; i += VJF_NT) { const float w = expf(iw_s[i]); iw_s[i] = -0.5f / (w * w); }
+    if (p.U_in_smem) {
+      const float* U_s = sm + p.s_U;
+      int nz = 0;
+      for (int r = warp; r < R; r += VJF_NWARP)
+        for (int c = lane; c < r; c += 32) nz |= (U_s[r * p.ldu + c] != 0.f);
+      if (nz) atomicOr(flag_s, 1);
+    }
+  }
   // ---- S1: xs = m_s + eps1 * exp(l_s / 2) (vjf/util.py:11-13); xu = [xs, u] (util.py:38-49) ----
   for (int i = tid; i < nb * du; i += VJF_NT) {
     const int b = i / du, k = i - b * du;
@@ -185,6 +278,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
   __syncthreads();
 
+  VJF_STAMP(p, t, 9);
   // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
   for (int b = warp; b < nb; b += VJF_NWARP) {
     for (int k = lane; k < Rp; k += 32) {
@@ -199,10 +293,11 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
   __syncthreads();
 
+  VJF_STAMP(p, t, 10);
   // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
   //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
   if (p.U_in_smem) {
-    mma_quadform(phi_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, u_upper);
+    mma_quadform(phi_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, *flag_s == 0);
   } else {
     const float* U = st + p.lay.w_chol;
     for (int b = warp; b < nb; b += VJF_NWARP) {
@@ -226,13 +321,16 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     }
   }
 
+  VJF_STAMP(p, t, 11);
   // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
   const float* hL; int ldh, HL;
   {
     const float* A = in_s; int lda = K1p, K = K1;
     for (int l = 0; l < L; ++l) {
       float* out = sm + p.s_act[l];
-      mma_linear_fwd(A, lda, K, st + p.lay.mlp_w[l], st + p.lay.mlp_b[l], p.H[l], out, p.Hp[l], rows, true);
+      const bool w_sm = (l == 0) && p.W1_in_smem;
+      mma_linear_fwd(A, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
+                     p.Hp[l], rows, true);
       // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
       const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
       if (h16 > h8)
@@ -242,6 +340,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     }
     hL = A; ldh = lda; HL = K;
   }
+  VJF_STAMP(p, t, 12);
   // p_logvar from the n-tile partial sums (qp_s complete after the barrier above)
   if (tid < nb) {
     float q = qp_s[tid];
@@ -253,11 +352,11 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     float my_m = 0.f, my_lv = 0.f;
     for (int k = 0; k < d; ++k) {
       float m = 0.f, lv = 0.f;
-      const float* wm = st + p.lay.head_m_w + k;
-      const float* wv = st + p.lay.head_v_w + k;
+      const float* wm = hm_s + k;
+      const float* wv = hv_s + k;
       for (int n = lane; n < HL; n += 32) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
       m = warp_sum(m); lv = warp_sum(lv);
-      if (lane == k) { my_m = m; my_lv = lv + st[p.lay.head_v_b + k]; }
+      if (lane == k) { my_m = m; my_lv = lv + hv_s[HL * d + k]; }
     }
     if (lane < d) {
       const int i = b * d + lane;
@@ -274,65 +373,20 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
   __syncthreads();
 
-  // ---- S5: decoder eta = D xt + bias (model.py:29-30), likelihood terms and dloss/deta (times B) ----
-  for (int b = warp; b < nb; b += VJF_NWARP) {
-    const float* xtb = xt_s + b * d;
-    const float* yb = in_s + b * K1p;
-    float* gb = g_s + b * Dp;
-    for (int j = lane; j < D; j += 32) {
-      float eta = db[j];
-      for (int k = 0; k < d; ++k) eta = fmaf(dw[k * D + j], xtb[k], eta);
-      const float yv = yb[j];
-      float g;
-      if (p.lik == VJF_LIK_GAUSSIAN) {
-        // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
-        const float r = yv - eta;
-        const float rs = yv * p_lam - eta * p_lam;
-        const float mse = rs * rs;
-        if (!isfinite(mse)) sc[SC_BADMSE] += 1.f;
-        sc[SC_RECON] += 0.5f * (mse + lam);
-        sc[SC_SSE] = fmaf(r, r, sc[SC_SSE]);
-        g = -r * e_nlam;
-        // d/dlambda = 0.5 (1 - r^2 e^-lambda) ; accumulated into the lik_logvar gradient slot
-        sc[6] += r_on ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
-      } else {
-        // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62
-        const float ec = fminf(eta, 10.0f);
-        const float ex = expf(ec);
-        sc[SC_RECON] += ex - yv * ec;
-        g = (eta <= 10.0f) ? (ex - yv) : 0.f;
-        if (eta != eta) { sc[SC_RECON] = eta; g = eta; }  // NaN propagates like torch.clamp
-      }
-      gb[j] = r_on ? g : 0.f;
-    }
+  VJF_STAMP(p, t, 13);
+  // ---- S5/S6: decoder eta = D xt + bias (model.py:29-30), likelihood terms, dloss/deta (times B), g_xt = g_eta D,
+  //      decoder gradients.  Specialised on the state dimension so that xt and the accumulators live in registers.
+  switch (d) {
+    case 1: decoder_stage<1>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+    case 2: decoder_stage<2>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+    case 3: decoder_stage<3>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+    case 4: decoder_stage<4>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+    default: if (d <= 8) decoder_stage<8>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
+             else decoder_stage<16>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
   }
   __syncthreads();
 
-  // ---- S6: decoder gradients and g_xt = g_eta D ----
-  {
-    float* gdw = slot + p.lay.dec_w;
-    float* gdb = slot + p.lay.dec_b;
-    for (int j = tid; j < D; j += VJF_NT) {
-      float accb = 0.f;
-      for (int b = 0; b < nb; ++b) accb += g_s[b * Dp + j];
-      acc_store(gdb + j, accb, first);
-      for (int k = 0; k < d; ++k) {
-        float acc = 0.f;
-        for (int b = 0; b < nb; ++b) acc = fmaf(g_s[b * Dp + j], xt_s[b * d + k], acc);
-        acc_store(gdw + k * D + j, acc, first);
-      }
-    }
-    for (int b = warp; b < nb; b += VJF_NWARP) {
-      for (int k = 0; k < d; ++k) {
-        float acc = 0.f;
-        for (int j = lane; j < D; j += 32) acc = fmaf(g_s[b * Dp + j], dw[k * D + j], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) gxt_s[b * d + k] = acc;
-      }
-    }
-  }
-  __syncthreads();
-
+  VJF_STAMP(p, t, 15);
   // ---- S7: dynamics NLL (functional.py:55-75 via model.py:390-391), entropy (functional.py:25-29),
   //      g_mt and g_lt (times B) ----
   for (int i = tid; i < nb * d; i += VJF_NT) {
@@ -352,6 +406,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
   __syncthreads();
 
+  VJF_STAMP(p, t, 16);
   // ---- S8: backward through the heads and the MLP ----
   {
     // head weight gradients [H_L][d] (input-major) and logvar-head bias
@@ -368,8 +423,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       acc_store(slot + p.lay.head_v_b + lane, s, first);
     }
     // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2); pad columns up to a multiple of 8 are zero
-    const float* wm = st + p.lay.head_m_w;
-    const float* wv = st + p.lay.head_v_w;
+    const float* wm = hm_s;
+    const float* wv = hv_s;
     const int H8 = (HL + 7) & ~7;
     for (int b = warp; b < nb; b += VJF_NWARP) {
       for (int n = lane; n < H8; n += 32) {
@@ -384,6 +439,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       }
     }
     __syncthreads();
+    VJF_STAMP(p, t, 17);
     float* gcur = gpa; float* gnext = gpb;
     for (int l = L - 1; l >= 0; --l) {
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
@@ -412,6 +468,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     }
   }
 
+  VJF_STAMP(p, t, 18);
   // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
   mma_gram(phi_s, Rp, R, rows, slot + p.pa, first);
   {
@@ -424,6 +481,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     }
   }
 
+  VJF_STAMP(p, t, 19);
   // ---- scalar sums of the tile ----
 #pragma unroll
   for (int i = 0; i < VJF_NSCAL; ++i) {
@@ -438,46 +496,49 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     else acc_store(slot + p.ps + tid, s, first);
   }
   __syncthreads();
+  VJF_STAMP(p, t, 20);
 }
 
-// Load the parameters every tile of this step shares into shared memory.  Returns (block-uniform) whether
-// w_chol is upper triangular, which lets the quadratic form skip the zero blocks.
-static __device__ int phase_a_prologue(const StepParams& p, float* sm) {
+// Start the asynchronous staging (cp.async) of every parameter the tiles of this step share; the first tile
+// waits for it after it has issued its own observation loads, so the two overlap.
+static __device__ void phase_a_prologue(const StepParams& p, float* sm) {
   const int tid = threadIdx.x;
   const float* st = p.state;
-  float* W_s = sm + p.s_W; float* c_s = sm + p.s_c; float* iw_s = sm + p.s_iw;
-  for (int i = tid; i < p.R * p.d; i += VJF_NT) W_s[i] = st[p.lay.w_mean + i];
-  for (int i = tid; i < p.R * p.du; i += VJF_NT) c_s[i] = st[p.lay.centroid + i];
-  for (int i = tid; i < p.R; i += VJF_NT) { const float w = expf(st[p.lay.logwidth + i]); iw_s[i] = -0.5f / (w * w); }
+  const int HL = p.H[p.L - 1];
+  stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
+  stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
+  stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
+  stage_async(sm + p.s_hm, p.d, st + p.lay.head_m_w, p.d, HL, p.d, tid, VJF_NT);
+  stage_async(sm + p.s_hv, p.d, st + p.lay.head_v_w, p.d, HL, p.d, tid, VJF_NT);
+  stage_async(sm + p.s_hv + HL * p.d, p.d, st + p.lay.head_v_b, p.d, 1, p.d, tid, VJF_NT);
   if (p.dec_in_smem) {
-    float* dec = sm + p.s_dec;
-    for (int i = tid; i < p.d * p.D; i += VJF_NT) dec[i] = st[p.lay.dec_w + i];
-    for (int i = tid; i < p.D; i += VJF_NT) dec[p.d * p.D + i] = st[p.lay.dec_b + i];
+    stage_async(sm + p.s_dec, p.D, st + p.lay.dec_w, p.D, p.d, p.D, tid, VJF_NT);
+    stage_async(sm + p.s_dec + p.d * p.D, p.D, st + p.lay.dec_b, p.D, 1, p.D, tid, VJF_NT);
   }
-  int lower_nonzero = 0;
   if (p.U_in_smem) {
     float* U_s = sm + p.s_U;
     const int Rk = (p.R + 7) & ~7, ldu = p.ldu;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < Rk; r += VJF_NWARP) {
-      for (int c = lane; c < ldu; c += 32) {
-        float v = 0.f;
-        if (r < p.R && c < p.R) { v = st[p.lay.w_chol + r * p.R + c]; if (c < r && v != 0.f) lower_nonzero = 1; }
-        U_s[r * ldu + c] = v;
-      }
-    }
+    stage_async(U_s, ldu, st + p.lay.w_chol, p.R, p.R, p.R, tid, VJF_NT);
+    // zero padding (disjoint from the async destinations)
+    for (int i = tid; i < Rk * ldu; i += VJF_NT) { const int r = i / ldu, c = i - r * ldu; if (r >= p.R || c >= p.R) U_s[i] = 0.f; }
   }
-  return !__syncthreads_or(lower_nonzero);
+  if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
+  cp_async_commit();
+  if (tid == 0) *reinterpret_cast<int*>(sm + p.s_flag) = 0;
 }
 
 static __device__ void phase_a(const StepParams& p, float* sm, int t, unsigned masks) {
-  const int u_upper = phase_a_prologue(p, sm);
+  VJF_STAMP(p, t, 7);
+  __syncthreads();  // the previous phase is done with the shared memory that is re-planned here
+  phase_a_prologue(p, sm);
+  VJF_STAMP(p, t, 21);
   bool first = true;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    phase_a_tile(p, sm, t, tile, first, masks, u_upper);
+    phase_a_tile(p, sm, t, tile, first, masks);
     first = false;
   }
   if (first) {  // a CTA without tiles still owns a slot: zero it
+    cp_async_wait_all();
     float* slot = p.partials + (size_t)blockIdx.x * p.PS;
     for (int i = threadIdx.x; i < p.PS; i += VJF_NT) slot[i] = 0.f;
   }
@@ -575,111 +636,129 @@ static __device__ double block_sum_d(double v, double* red) {
 // r % 16 (register slot r / 16), column j in lane j % 32 (slot j / 32): the sweep touches shared memory only
 // to broadcast the current column.  Returns false (block-uniform) if a pivot is not positive.
 template <int CPL, int RPW>
-static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv) {
+static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv, int t) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, d = p.d, NR = 2 * R + d;
-  const int NRp = (NR + 3) & ~3;
-  float* colbuf = sm;                           // [2][NRp]
-  float* dvec = colbuf + 2 * NRp;               // [R]
+  constexpr int NRP = VJF_NWARP * RPW;          // rows incl. padding: every (warp, slot) pair is a row
+  float* colbuf = sm;                           // [2][NRP]
+  float* dvec = colbuf + 2 * NRP;               // [R]
   float* zbuf = dvec + ((R + 3) & ~3);          // [d][R]   g, later z = L^-1 g
-  float* wbuf = zbuf + ((d * R + 3) & ~3);      // [R][d]   W'
-  float* misc = wbuf + ((d * R + 3) & ~3);      // [0..1] 1/pivot (double buffered), [2] fail flag
+  float* Ws = zbuf + ((d * R + 3) & ~3);        // [R][d]   old W staged
+  float* bs = Ws + ((d * R + 3) & ~3);          // [R][d]   b staged
+  float* misc = bs + ((d * R + 3) & ~3);        // [0..1] 1/pivot (double buffered), [2] fail flag
   float* st = p.state;
   const float* P = st + p.lay.w_precision;
-  const float* W = st + p.lay.w_mean;
   float v[RPW][CPL];
   float v0[(RPW + 1) / 2][CPL];                 // P' rows kept for the commit (P rows occupy the first slots)
-  if (tid == 0) misc[2] = 0.f;
+  const int rpw_used = (NR + VJF_NWARP - 1) / VJF_NWARP;
+  // ---- issue every global load first (P rows, A rows, W, b), then compute ----
+  float a_in[(RPW + 1) / 2][CPL];
 #pragma unroll
-  for (int ri = 0; ri < RPW; ++ri) {
+  for (int ri = 0; ri < (RPW + 1) / 2; ++ri) {
     const int r = warp + VJF_NWARP * ri;
 #pragma unroll
-    for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = 0.f;
-    if (r < R) {
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      const bool ok = (r < R) && (j < R);
+      v[ri][ci] = ok ? P[r * R + j] : 0.f;
+      a_in[ri][ci] = (ok && j <= r) ? A[r * R + j] : 0.f;  // lower triangle of the symmetric A
+    }
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) { Ws[i] = st[p.lay.w_mean + i]; bs[i] = bv[i]; }
+  if (tid == 0) misc[2] = 0.f;
+  __syncthreads();
 #pragma unroll
-      for (int ci = 0; ci < CPL; ++ci) {
-        const int j = lane + 32 * ci;
-        v[ri][ci] = (j < R) ? P[r * R + j] : 0.f;
-      }
+  for (int ri = 0; ri < (RPW + 1) / 2; ++ri) {
+    const int r = warp + VJF_NWARP * ri;
+    if (r < R) {
       // g[r][c] = sum_j P[r][j] W[j][c] + b[r][c]/v   (old P, old W: module.py:93)
       for (int c = 0; c < d; ++c) {
         float s = 0.f;
 #pragma unroll
         for (int ci = 0; ci < CPL; ++ci) {
           const int j = lane + 32 * ci;
-          if (j < R) s = fmaf(v[ri][ci], W[j * d + c], s);
+          if (j < R) s = fmaf(v[ri][ci], Ws[j * d + c], s);
         }
         s = warp_sum(s);
-        if (lane == 0) zbuf[c * R + r] = fmaf(bv[r * d + c], iv, s);
+        if (lane == 0) zbuf[c * R + r] = fmaf(bs[r * d + c], iv, s);
       }
 #pragma unroll
       for (int ci = 0; ci < CPL; ++ci) {
-        const int j = lane + 32 * ci;
-        if (j <= r) v[ri][ci] = fmaf(A[r * R + j], iv, v[ri][ci]);  // lower triangle of the symmetric A
-        if (ri < (RPW + 1) / 2) v0[ri][ci] = v[ri][ci];
+        v[ri][ci] = fmaf(a_in[ri][ci], iv, v[ri][ci]);   // P' = P + A/v on and below the diagonal
+        v0[ri][ci] = v[ri][ci];
       }
     }
   }
+#pragma unroll
+  for (int ri = (RPW + 1) / 2; ri < RPW; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = 0.f;
+  VJF_STAMP(p, t, 25);
   __syncthreads();
 #pragma unroll
   for (int ri = 0; ri < RPW; ++ri) {
     const int r = warp + VJF_NWARP * ri;
-    if (r >= R && r < NR) {
+    if (r >= R) {
 #pragma unroll
       for (int ci = 0; ci < CPL; ++ci) {
         const int j = lane + 32 * ci;
-        if (r < R + d) v[ri][ci] = (j < R) ? zbuf[(r - R) * R + j] : 0.f;
-        else v[ri][ci] = (j == r - R - d) ? 1.0f : 0.f;
+        float x = 0.f;
+        if (r < R + d) x = (j < R) ? zbuf[(r - R) * R + j] : 0.f;
+        else if (r < NR) x = (j == r - R - d) ? 1.0f : 0.f;
+        v[ri][ci] = x;
       }
     }
   }
   // publish column 0 and 1/pivot_0
-  {
+  if (lane == 0) {
 #pragma unroll
-    for (int ri = 0; ri < RPW; ++ri) {
-      const int r = warp + VJF_NWARP * ri;
-      if (lane == 0 && r < NR) colbuf[r] = v[ri][0];
-    }
-    if (warp == 0 && lane == 0) { const float pv = v[0][0]; misc[0] = 1.0f / pv; if (!(pv > 0.f)) misc[2] = 1.f; }
+    for (int ri = 0; ri < RPW; ++ri) colbuf[warp + VJF_NWARP * ri] = v[ri][0];
+    if (warp == 0) { const float pv = v[0][0]; misc[0] = 1.0f / pv; if (!(pv > 0.f)) misc[2] = 1.f; }
   }
   __syncthreads();
+  VJF_STAMP(p, t, 26);
+  // ---- the sweep.  No row predicates are needed: rows above the pivot only touch their (unused) upper
+  //      triangle, and an identity row whose column has not been reached has a zero multiplier. ----
   int kb = 0;
   bool fail = false;
   for (int k = 0; k < R; ++k) {
-    const float* cb = colbuf + kb * NRp;
+    const float* cb = colbuf + kb * NRP;
+    float* cbn = colbuf + (kb ^ 1) * NRP;
     if (misc[2] != 0.f) { fail = true; break; }
     const float inv = misc[kb];
     if (tid == 0) dvec[k] = cb[k];
     float cj[CPL];
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) { const int j = lane + 32 * ci; cj[ci] = (j > k && j < R) ? cb[j] : 0.f; }
-    const int kn = k + 1, ln = kn & 31, cn = kn >> 5;
-    float* cbn = colbuf + (kb ^ 1) * NRp;
 #pragma unroll
     for (int ri = 0; ri < RPW; ++ri) {
-      const int r = warp + VJF_NWARP * ri;
-      // active rows: below the pivot row; identity row c only once column c has been reached
-      const bool active = (r > k) && (r < NR) && !(r >= R + d && r - R - d > k);
-      if (active) {
-        const float tk = cb[r] * inv;
+      if (ri < rpw_used) {
+        const float tk = cb[warp + VJF_NWARP * ri] * inv;
 #pragma unroll
-        for (int ci = 0; ci < CPL; ++ci) {
-          const int j = lane + 32 * ci;
-          if (r >= R || j <= r) v[ri][ci] = fmaf(-tk, cj[ci], v[ri][ci]);
-        }
+        for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = fmaf(-tk, cj[ci], v[ri][ci]);
       }
-      if (kn < R && lane == ln && r < NR) {
+    }
+    const int kn = k + 1;
+    if (kn < R && lane == (kn & 31)) {
+      const int cn = kn >> 5;
+#pragma unroll
+      for (int ri = 0; ri < RPW; ++ri) {
         float x = v[ri][0];
 #pragma unroll
         for (int ci = 1; ci < CPL; ++ci) x = (cn == ci) ? v[ri][ci] : x;
-        cbn[r] = x;
-        if (r == kn) { misc[kb ^ 1] = 1.0f / x; if (!(x > 0.f)) misc[2] = 1.f; }
+        cbn[warp + VJF_NWARP * ri] = x;
+      }
+      if (warp == (kn & (VJF_NWARP - 1))) {
+        const float x = cbn[kn];
+        misc[kb ^ 1] = 1.0f / x;
+        if (!(x > 0.f)) misc[2] = 1.f;
       }
     }
     __syncthreads();
     kb ^= 1;
   }
   if (!fail && misc[2] != 0.f) fail = true;
+  VJF_STAMP(p, t, 27);
   if (fail) return false;
   __syncthreads();
   // ---- scale the columns and commit: w_pchol = L, w_chol = L^-T, z ; then W' = w_chol z ----
@@ -715,6 +794,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     }
   }
   __syncthreads();
+  VJF_STAMP(p, t, 28);
   float* Wout = st + p.lay.w_mean;
 #pragma unroll
   for (int ri = 0; ri < RPW; ++ri) {
@@ -729,7 +809,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
           if (j < R) s = fmaf(v[ri][ci], zbuf[i * R + j], s);
         }
         s = warp_sum(s);
-        if (lane == 0) Wout[c * d + i] = s;
+        if (lane == 0) { Wout[c * d + i] = s; Ws[c * d + i] = s; }
       }
     }
   }
@@ -850,6 +930,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
       st[p.lay.lik_n] = n_new;
     }
   }
+  VJF_STAMP(p, t, 24);
   if (!upd) return;
   const float gam = st[p.lay.tr_logvar];
   // rls(x, target, v): v = exp(state logvar) in a filter step (model.py:371); in initialize v is the
@@ -858,12 +939,13 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   __syncthreads();
   if (!warm) {
     bool ok;
-    if (R <= 64) ok = rls_factor_regs<2, 9>(p, sm, iv, A, bv);
-    else if (R <= 128) ok = rls_factor_regs<4, 17>(p, sm, iv, A, bv);
+    if (R <= 64) ok = rls_factor_regs<2, 9>(p, sm, iv, A, bv, t);
+    else if (R <= 128) ok = rls_factor_regs<4, 17>(p, sm, iv, A, bv, t);
     else ok = rls_factor_smem(p, sm, iv, A, bv);
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
   }
+  VJF_STAMP(p, t, 29);
 
   // ---- state-noise running variance (vjf/model.py:373-377).  sum |dx - phi W'|^2 from the reduced
   //      statistics: S - 2 <W', b> + <W', A W'>, evaluated in double ----
