@@ -214,13 +214,20 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
 
     # ---- warm-up (also brings the clocks up from idle) ----
+    # The information-form RLS accumulates phi^T phi / v without forgetting (shrink = 1, vjf/model.py:371);
+    # in fp32 -- the reference's dtype too -- it degrades after a few 1e6 samples.  Every timed region
+    # therefore starts from the initial parameters, like the first epochs of a fit().
+    state0 = model._flat.clone()
     for _ in range(max(3, args.warmup)):
         step_dev()
     torch.cuda.synchronize()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < args.spinup:
+        model._flat.copy_(state0)
         step_dev()
         torch.cuda.synchronize()
+    model._flat.copy_(state0)
+    model.status()
 
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local)
@@ -241,8 +248,9 @@ def run_ours(args, cfg):
     status = model.status()
 
     # ---- timed region: end to end through the C ABI with pinned host buffers ----
-    for _ in range(2):
-        step_e2e()
+    model._flat.copy_(state0)
+    step_e2e()
+    model._flat.copy_(state0)
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
@@ -273,7 +281,8 @@ def run_ours(args, cfg):
                "e2e": {"value": units / e2e_s, "unit": "trial-steps/s", "h2d_bytes_per_step": int(y_host.numel() * 4),
                        "d2h_bytes_per_step": int((mu_h.numel() + lv_h.numel() + ls_h.numel()) * 4),
                        "api": "vjf_run_host (C ABI, pinned host buffers, chunked H2D overlapped with compute)"},
-               "gpu_launches": int(launches), "clocks": clocks, "status_word": int(status)}
+               "gpu_launches": int(launches), "clocks": clocks, "status_word": int(status),
+               "status_word_e2e": int(model.status())}
         if world == 1 and not args.no_cpu:
             val, dt = cpu_port_rate(cfg, B, args.cpu_steps)
             out["cpu_baseline"] = {"value": val, "unit": "trial-steps/s", "cores": os.cpu_count(), "kind": "port",

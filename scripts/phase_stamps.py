@@ -9,8 +9,10 @@ D, d, R, H = int(os.environ.get("PD", 200)), int(os.environ.get("Pd", 3)), int(o
 lib = _lib.load()
 m = VJF.make_model(D, d, 0, R, H, os.environ.get("PLIK", "poisson"), max_trials=B)
 y = torch.poisson(torch.full((T, B, D), 0.5, device="cuda"))
+warm = VJF.make_model(D, d, 0, R, H, os.environ.get("PLIK", "poisson"), max_trials=B)
 for _ in range(20):
-    m.run(y)
+    warm.run(y)   # brings the clocks up; the measured model below starts from fresh RLS state
+m.run(y[:8])
 torch.cuda.synchronize()
 dbg = torch.zeros(T, 64, dtype=torch.int64, device="cuda")
 lib.vjf_debug_set_stamps.argtypes = [C.c_void_p]; lib.vjf_debug_set_stamps.restype = None
@@ -19,20 +21,23 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); m.run(y); e1.record(); torch.cuda.synchronize()
 lib.vjf_debug_set_stamps(None)
 s = dbg.cpu().double()
-names = ["phaseA", "barrier1", "B1(reduce+sgd)", "barrier2", "B2(rls)", "barrier3"]
-dif = (s[:, 1:7] - s[:, 0:6])[4:]  # skip first steps
-print(f"B={B} D={D} R={R} H={H}: event time per step {e0.elapsed_time(e1)/T*1e3:.1f} us; step (stamps) {(s[-1,6]-s[4,0]).item()/(T-4)/1e3:.1f} us")
+ov = bool((s[5:, 22] > s[5:, 4]).all())  # front stamps of step t+1 land after barrier 2 of step t => overlapped schedule
+names = ["back(t) | phaseA", "barrier1", "B1(reduce+sgd)", "barrier2", "B2(rls) || front(t+1)", "barrier3"]
+dif = (s[:, 1:7] - s[:, 0:6])[4:-1]
+print(f"B={B} D={D} R={R} H={H}: event time per step {e0.elapsed_time(e1)/T*1e3:.1f} us; step (stamps) {(s[-1,6]-s[4,0]).item()/(T-4)/1e3:.1f} us; overlapped={ov} status={m.status()}")
 for i, n in enumerate(names):
-    print(f"  {n:16s} mean {dif[:, i].mean().item()/1e3:7.2f} us   min {dif[:, i].min().item()/1e3:7.2f}  max {dif[:, i].max().item()/1e3:7.2f}")
-
-iv = [(7, 21, "prologue issue"), (21, 22, "S0 tile loads issue"), (22, 23, "cp.async wait"), (23, 8, "sync"), (8, 9, "S1 xs (+finish params)"), (9, 10, "S2 phi"), (10, 11, "S3 quadform+pm"), (11, 12, "S4 mlp fwd"),
-      (12, 13, "plv+heads+xt"), (13, 15, "S5/S6 decoder+grads"), (15, 16, "S7 dyn/entropy"), (16, 17, "S8 heads bwd+gpre"),
-      (17, 18, "wgrad+colsum"), (18, 19, "S9 gram+b"), (19, 20, "scalars")]
-print(" phase A stages (first tile of CTA 0):")
-for i, j, n in iv:
-    print(f"  {n:26s} {(s[4:, j] - s[4:, i]).mean().item()/1e3:7.2f} us")
+    print(f"  {n:24s} mean {dif[:, i].mean().item()/1e3:7.2f} us   min {dif[:, i].min().item()/1e3:7.2f}  max {dif[:, i].max().item()/1e3:7.2f}")
+front = [(22, 8, "S0 tile loads + cp.async wait"), (8, 9, "S1 xs"), (9, 11, "S2 phi"), (11, 12, "S4 mlp fwd"), (12, 13, "heads+xt"),
+         (13, 18, "S5/S6 decoder+grads"), (18, 19, "S9 gram+b")]
+back = [(10, 15, "S3 quadform+pm+plv"), (15, 16, "S7 dyn/entropy"), (16, 17, "S8 heads bwd+gpre"), (17, 20, "wgrad+colsum+scalars")]
+print(" front half (first trial CTA):")
+for i, j, n in front:
+    print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
+print(" back half:")
+for i, j, n in back:
+    print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
 b2 = [(4, 24, "losses/lik"), (24, 25, "load P,A,W,b + g"), (25, 26, "rows init+publish"), (26, 27, "LDL sweep"), (27, 28, "scale+commit"),
       (28, 29, "W'=Uz"), (29, 5, "residual/var")]
-print(" phase B2 stages:")
+print(" phase B2 stages (CTA 0):")
 for i, j, n in b2:
-    print(f"  {n:26s} {(s[4:, j] - s[4:, i]).mean().item()/1e3:7.2f} us")
+    print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")

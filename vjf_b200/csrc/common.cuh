@@ -37,7 +37,7 @@ struct StepParams {
   int TB, ntiles, nslots;
   // ---- shared-memory plan (float offsets) ----
   int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
-      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_total;
+      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_scf, s_b1, s_total;
   int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
@@ -62,6 +62,7 @@ struct StepParams {
   int T;
   int red_begin;   // first element of the partial vector the reduction touches
   long long* dbg;  // optional [T][8] per-phase globaltimer stamps of CTA 0 (development aid)
+  int overlap;     // persistent schedule: CTA 0 is the dedicated RLS CTA, trial CTAs run the front half of step t+1 beside it
   int init_mode;   // phase B2 runs as RBFDS.initialize (vjf/model.py:379-388) instead of a filter step
 };
 
@@ -162,10 +163,12 @@ __device__ __forceinline__ long long gtime_ns() {
   return t;
 }
 
-// development aid: CTA 0 / thread 0 drops a globaltimer stamp into slot idx of step t (64 slots per step)
+// development aid: thread 0 of CTA 0 (phase-A stage stamps 7..23: of the first trial CTA) drops a globaltimer
+// stamp into slot idx of step t (64 slots per step)
 #define VJF_STAMP(p, t, idx)                                                              \
   do {                                                                                    \
-    if ((p).dbg && blockIdx.x == 0 && threadIdx.x == 0) (p).dbg[(t) * 64 + (idx)] = gtime_ns(); \
+    if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (idx) >= 7 && (idx) <= 23) ? 1 : 0)) \
+      (p).dbg[(t) * 64 + (idx)] = gtime_ns();                                             \
   } while (0)
 
 // clamp that propagates NaN the way torch.clamp does (fminf/fmaxf would drop it)

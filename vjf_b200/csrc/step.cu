@@ -30,15 +30,36 @@ __device__ __forceinline__ unsigned base_masks(const StepParams& p) {
   return 1u | ((p.flags & VJF_FLAG_WARMUP) ? 0u : 2u) | 4u;
 }
 
-// The whole time loop in one cooperative launch: T x {phase A | barrier | B1 | barrier | B2 | barrier}.
+// The whole time loop in one cooperative launch.
+//
+// Plain schedule (several tiles per CTA):   T x { A | bar | B1 | bar | B2 (CTA 0) | bar }
+// Overlapped schedule (one tile per trial CTA, CTA 0 dedicated to the RLS):
+//     front(0) ; T x { back(t) | bar | B1(t) | bar | { CTA 0: B2(t)  ||  trial CTAs: front(t+1) } | bar }
+// front(t+1) needs only the SGD-updated parameters (B1), not the RLS outputs, so it hides behind the
+// serial factorisation of step t.
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float sm[];
   unsigned target = 0;
+  const bool trial_cta = blockIdx.x > 0;
+  if (p.overlap) {
+    if (!trial_cta) {
+      float* slot = p.partials;  // CTA 0 owns no trials: its slot stays zero
+      for (int i = threadIdx.x; i < p.PS; i += VJF_NT) slot[i] = 0.f;
+    } else {
+      phase_a_prologue(p, sm, STAGE_FRONT);
+      phase_a_tile(p, sm, 0, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+    }
+  }
   for (int t = 0; t < p.T; ++t) {
     unsigned masks = base_masks(p), fin;
     VJF_STAMP(p, t, 0);
     for (int attempt = 0;; ++attempt) {
-      phase_a(p, sm, t, masks);
+      if (!p.overlap) {
+        phase_a(p, sm, t, masks);
+      } else if (trial_cta) {
+        phase_a_prologue(p, sm, STAGE_BACK);
+        phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK);
+      }
       VJF_STAMP(p, t, 1);
       grid_barrier(p.barrier, target);
       VJF_STAMP(p, t, 2);
@@ -49,6 +70,10 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       if (attempt == 0 && nm != masks && (p.flags & VJF_FLAG_SGD)) {
         masks = nm;
         grid_barrier(p.barrier, target);
+        if (p.overlap && trial_cta) {
+          phase_a_prologue(p, sm, STAGE_FRONT);
+          phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_FRONT);
+        }
         continue;
       }
       break;
@@ -57,7 +82,12 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
     VJF_STAMP(p, t, 3);
     grid_barrier(p.barrier, target);
     VJF_STAMP(p, t, 4);
-    if (blockIdx.x == 0) phase_b2(p, sm, t, fin);
+    if (blockIdx.x == 0) {
+      phase_b2(p, sm, t, fin);
+    } else if (p.overlap && t + 1 < p.T) {
+      phase_a_prologue(p, sm, STAGE_FRONT);
+      phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+    }
     VJF_STAMP(p, t, 5);
     grid_barrier(p.barrier, target);
     VJF_STAMP(p, t, 6);
@@ -180,6 +210,8 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_hm = take((size_t)p.H[p.L - 1] * p.d);
   p.s_hv = take((size_t)p.H[p.L - 1] * p.d + p.d);
   p.s_flag = take(4);
+  p.s_scf = take(VJF_NSCAL);
+  p.s_b1 = take(512 + 8);
   p.s_W = take((size_t)p.R * p.d);
   p.s_c = take((size_t)p.R * p.du);
   p.s_iw = take((size_t)p.R);
@@ -187,14 +219,18 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   const size_t a = off;
   // phase B2: register path needs ~2(2R+d) + R + 2dR floats; the shared-memory fallback (R > 128)
   // [(2R+d)][ldm] + pivots; phase B1: 512 floats
-  size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8;
+  size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
   p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
   return (size_t)p.s_total;
 }
 
-static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots) {
+// persistent != 0: plan for the cooperative kernel, where CTA 0 is the dedicated RLS CTA whenever every trial CTA
+// gets exactly one tile (the overlapped schedule)
+static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots, int persistent = 0) {
   if (B < 1 || B > h->cfg.max_trials) { vjf_set_error("trials B=%d outside [1, max_trials=%d]", B, h->cfg.max_trials); return -1; }
+  p.overlap = 0;
+  if (persistent && max_slots > 1 && (B + VJF_TB_MAX - 1) / VJF_TB_MAX <= max_slots - 1) { p.overlap = 1; max_slots -= 1; }
   const int want = std::min(std::max((int)up((B + max_slots - 1) / max_slots, 4), 4), VJF_TB_MAX);
   const size_t limit = h->smem_limit;
   bool u_smem = (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
@@ -214,7 +250,8 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots) {
   p.B = B;
   p.TB = tb;
   p.ntiles = (B + tb - 1) / tb;
-  p.nslots = std::min(p.ntiles, max_slots);
+  if (p.overlap && p.ntiles > max_slots) p.overlap = 0;  // the tile had to shrink to fit shared memory
+  p.nslots = p.overlap ? p.ntiles + 1 : std::min(p.ntiles, max_slots + (persistent && max_slots < h->max_slots ? 1 : 0));
   return 0;
 }
 
@@ -360,7 +397,7 @@ extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32
   if (T < 1) { vjf_set_error("T must be >= 1"); return -1; }
   if (y_dtype != VJF_Y_F32 && y_dtype != VJF_Y_U8) { vjf_set_error("unknown y dtype"); return -1; }
   StepParams p = h->base;
-  if (plan_tiles(h, p, B, h->max_slots)) return -1;
+  if (plan_tiles(h, p, B, h->max_slots, 1)) return -1;
   p.Bglobal = B;
   p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
   p.mu = mu; p.logvar = logvar; p.losses = losses;

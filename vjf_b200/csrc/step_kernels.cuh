@@ -170,21 +170,30 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
   }
 }
 
-// masks: bit0 recon term on, bit1 dynamics term on (already combined with !warm_up), bit2 entropy term on
-static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks) {
+// masks: bit0 recon term on, bit1 dynamics term on (already combined with !warm_up), bit2 entropy term on.
+// part: PART_BOTH runs the whole tile; PART_FRONT / PART_BACK run the halves of the overlapped schedule:
+//   front = everything that does not need the RLS outputs of the previous step (observation staging, RBF
+//           features, recognition forward, decoder + likelihood + their gradients, RLS statistics)
+//   back  = dynamics read-out with the fresh w_mean / w_chol / state noise, ELBO dynamics + entropy terms,
+//           backward through the recognition network
+#define PART_BOTH 0
+#define PART_FRONT 1
+#define PART_BACK 2
+static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
-  const int K1 = p.K1, K1p = p.K1p, Dp = p.Dp, Rp = p.Rp, Gp = p.Gp;
+  const int K1 = p.K1, K1p = p.K1p, Rp = p.Rp, Gp = p.Gp;
   const int b0 = tile * p.TB;
   const int nb = min(p.TB, p.B - b0);
   const int rows = (nb + 15) & ~15;
-  float* in_s = sm + p.s_in;   float* g_s = sm + p.s_g;     float* phi_s = sm + p.s_phi;
+  float* in_s = sm + p.s_in;   float* phi_s = sm + p.s_phi;
   float* gpa = sm + p.s_gpa;   float* gpb = sm + p.s_gpb;   float* eps_s = sm + p.s_eps;
   float* xu_s = sm + p.s_xu;   float* xt_s = sm + p.s_xt;   float* mt_s = sm + p.s_mt;
   float* lt_s = sm + p.s_lt;   float* pm_s = sm + p.s_pm;   float* dx_s = sm + p.s_dx;
   float* gxt_s = sm + p.s_gxt; float* gmt_s = sm + p.s_gmt; float* glt_s = sm + p.s_glt;
   float* plv_s = sm + p.s_plv; float* W_s = sm + p.s_W;     float* c_s = sm + p.s_c;
   float* iw_s = sm + p.s_iw;   float* red_s = sm + p.s_red; float* qp_s = sm + p.s_qp;
+  float* scf_s = sm + p.s_scf;
   const float* hm_s = sm + p.s_hm; const float* hv_s = sm + p.s_hv;  // head weights [H_L][d], then head_v_b at hv_s[H_L*d]
   int* flag_s = reinterpret_cast<int*>(sm + p.s_flag);
   float* st = p.state;
@@ -192,108 +201,205 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   const float* db = p.dec_in_smem ? (sm + p.s_dec + d * D) : (st + p.lay.dec_b);  // [D]
   float* slot = p.partials + (size_t)blockIdx.x * p.PS;
   const bool r_on = masks & 1u, d_on = masks & 2u, h_on = masks & 4u;
-  const float lam = st[p.lay.lik_logvar], gam = st[p.lay.tr_logvar];
-  const float e_nlam = expf(-lam), e_ngam = expf(-gam), p_gam = expf(-0.5f * gam), p_lam = expf(-0.5f * lam);
+  const int HL = p.H[L - 1], ldh = p.Hp[L - 1];
+  const float* hL = sm + p.s_act[L - 1];
   float sc[VJF_NSCAL];
 #pragma unroll
   for (int i = 0; i < VJF_NSCAL; ++i) sc[i] = 0.f;
 
-  // ---- S0: stage the tile: in = [y | u | m_s | l_s | 0] (vjf/recognition.py:32-37), eps, zero pads ----
-  {
-    const size_t row0 = (size_t)t * p.B + b0;
-    const int Ep = K1p - D;  // u, m_s, l_s and the zero pad
-    const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
-    const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
-    const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-    for (int b = warp; b < rows; b += VJF_NWARP) {
-      float* dst = in_s + b * K1p;
-      if (b < nb) {
-        if ((D & 3) == 0) {
-          if (p.y_dtype == VJF_Y_U8) {
-            const uchar4* src = reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(p.y) + (row0 + b) * D);
-            for (int j = lane; j < (D >> 2); j += 32) {
-              const uchar4 v = src[j];
-              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  if (part != PART_BACK) {
+    const float lam = st[p.lay.lik_logvar];
+    const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
+    // ---- S0: stage the tile: in = [y | u | m_s | l_s | 0] (vjf/recognition.py:32-37), eps, zero pads ----
+    {
+      const size_t row0 = (size_t)t * p.B + b0;
+      const int Ep = K1p - D;  // u, m_s, l_s and the zero pad
+      const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
+      const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
+      const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
+      for (int b = warp; b < rows; b += VJF_NWARP) {
+        float* dst = in_s + b * K1p;
+        if (b < nb) {
+          if ((D & 3) == 0) {
+            if (p.y_dtype == VJF_Y_U8) {
+              const uchar4* src = reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(p.y) + (row0 + b) * D);
+              for (int j = lane; j < (D >> 2); j += 32) {
+                const uchar4 v = src[j];
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+              }
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.y) + (row0 + b) * D);
+              for (int j = lane; j < (D >> 2); j += 32) *reinterpret_cast<float4*>(dst + 4 * j) = src[j];
             }
           } else {
-            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.y) + (row0 + b) * D);
-            for (int j = lane; j < (D >> 2); j += 32) *reinterpret_cast<float4*>(dst + 4 * j) = src[j];
+            for (int j = lane; j < D; j += 32) dst[j] = load_y(p, (row0 + b) * D + j);
+          }
+          for (int e = lane; e < Ep; e += 32) {
+            float v = 0.f;
+            if (e < u) v = p.u_in[(row0 + b) * u + e];
+            else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
+            else if (e < E) v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
+            dst[D + e] = v;
+          }
+          if (p.eps) {
+            const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
+            for (int k = lane; k < 2 * d; k += 32) eps_s[b * 2 * d + k] = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d];
+          } else {
+            const int nblk = (d + 3) >> 2;
+            if (lane < 2 * nblk) {
+              const int which = lane / nblk, blk = lane - which * nblk;
+              float z[4];
+              philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
+              for (int k = 0; k < 4; ++k)
+                if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
+            }
           }
         } else {
-          for (int j = lane; j < D; j += 32) dst[j] = load_y(p, (row0 + b) * D + j);
+          // pad rows of everything that is summed over the rows of the tile
+          for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
+          for (int j = lane; j < Rp; j += 32) phi_s[b * Rp + j] = 0.f;
+          for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; }
+          for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
         }
-        for (int e = lane; e < Ep; e += 32) {
-          float v = 0.f;
-          if (e < u) v = p.u_in[(row0 + b) * u + e];
-          else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
-          else if (e < E) v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
-          dst[D + e] = v;
-        }
-        if (p.eps) {
-          const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
-          for (int k = lane; k < 2 * d; k += 32) eps_s[b * 2 * d + k] = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d];
-        } else {
-          const int nblk = (d + 3) >> 2;
-          if (lane < 2 * nblk) {
-            const int which = lane / nblk, blk = lane - which * nblk;
-            float z[4];
-            philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
-            for (int k = 0; k < 4; ++k)
-              if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
-          }
-        }
-      } else {
-        // pad rows of everything that is summed over the rows of the tile
-        for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
-        for (int j = lane; j < Rp; j += 32) phi_s[b * Rp + j] = 0.f;
-        for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; }
-        for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
       }
     }
-  }
-  VJF_STAMP(p, t, 22);
-  cp_async_wait_all();  // shared parameters staged by phase_a_prologue (no-op after the first tile)
-  VJF_STAMP(p, t, 23);
-  __syncthreads();
+    VJF_STAMP(p, t, 22);
+    cp_async_wait_all();  // shared parameters staged by the prologue (no-op after the first tile)
+    __syncthreads();
 
-  VJF_STAMP(p, t, 8);
-  if (first) {
-    // finish the staged parameters: 1/w^2 scaling of the RBF widths, and whether w_chol is upper triangular
-    for (int i = tid; i < R; i += VJF_NT) { const float w = expf(iw_s[i]); iw_s[i] = -0.5f / (w * w); }
-    if (p.U_in_smem) {
-      const float* U_s = sm + p.s_U;
-      int nz = 0;
-      for (int r = warp; r < R; r += VJF_NWARP)
-        for (int c = lane; c < r; c += 32) nz |= (U_s[r * p.ldu + c] != 0.f);
-      if (nz) atomicOr(flag_s, 1);
+    VJF_STAMP(p, t, 8);
+    if (first) {  // finish the staged RBF widths: -1/(2 w^2)
+      for (int i = tid; i < R; i += VJF_NT) { const float w = expf(iw_s[i]); iw_s[i] = -0.5f / (w * w); }
     }
-  }
-  // ---- S1: xs = m_s + eps1 * exp(l_s / 2) (vjf/util.py:11-13); xu = [xs, u] (util.py:38-49) ----
-  for (int i = tid; i < nb * du; i += VJF_NT) {
-    const int b = i / du, k = i - b * du;
-    float v;
-    if (k < d) v = in_s[b * K1p + D + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * in_s[b * K1p + D + u + d + k]);
-    else v = in_s[b * K1p + D + (k - d)];
-    xu_s[b * du + k] = v;
-  }
-  __syncthreads();
+    // ---- S1: xs = m_s + eps1 * exp(l_s / 2) (vjf/util.py:11-13); xu = [xs, u] (util.py:38-49) ----
+    for (int i = tid; i < nb * du; i += VJF_NT) {
+      const int b = i / du, k = i - b * du;
+      float v;
+      if (k < d) v = in_s[b * K1p + D + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * in_s[b * K1p + D + u + d + k]);
+      else v = in_s[b * K1p + D + (k - d)];
+      xu_s[b * du + k] = v;
+    }
+    __syncthreads();
 
-  VJF_STAMP(p, t, 9);
-  // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
-  for (int b = warp; b < nb; b += VJF_NWARP) {
-    for (int k = lane; k < Rp; k += 32) {
-      float v = 0.f;
-      if (k < R) {
-        float d2 = 0.f;
-        for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
-        v = expf(d2 * iw_s[k]);
+    VJF_STAMP(p, t, 9);
+    // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      for (int k = lane; k < Rp; k += 32) {
+        float v = 0.f;
+        if (k < R) {
+          float d2 = 0.f;
+          for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
+          v = expf(d2 * iw_s[k]);
+        }
+        phi_s[b * Rp + k] = v;
       }
-      phi_s[b * Rp + k] = v;
     }
-  }
-  __syncthreads();
 
+    VJF_STAMP(p, t, 11);
+    // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
+    {
+      const float* A = in_s; int lda = K1p, K = K1;
+      for (int l = 0; l < L; ++l) {
+        float* out = sm + p.s_act[l];
+        const bool w_sm = (l == 0) && p.W1_in_smem;
+        mma_linear_fwd(A, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
+                       p.Hp[l], rows, true);
+        // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
+        const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
+        if (h16 > h8)
+          for (int i = tid; i < rows * (h16 - h8); i += VJF_NT) out[(i / (h16 - h8)) * p.Hp[l] + h8 + i % (h16 - h8)] = 0.f;
+        __syncthreads();
+        A = out; lda = p.Hp[l]; K = p.H[l];
+      }
+    }
+    VJF_STAMP(p, t, 12);
+    // heads: m_t = W_m h (no bias), l_t = W_v h + b_v ; then xt = m_t + eps2 exp(l_t/2), dx = xt - xs
+    for (int b = warp; b < nb; b += VJF_NWARP) {
+      float my_m = 0.f, my_lv = 0.f;
+      for (int k = 0; k < d; ++k) {
+        float m = 0.f, lv = 0.f;
+        const float* wm = hm_s + k;
+        const float* wv = hv_s + k;
+        for (int n = lane; n < HL; n += 32) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
+        m = warp_sum(m); lv = warp_sum(lv);
+        if (lane == k) { my_m = m; my_lv = lv + hv_s[HL * d + k]; }
+      }
+      if (lane < d) {
+        const int i = b * d + lane;
+        mt_s[i] = my_m; lt_s[i] = my_lv;
+        const float x = my_m + eps_s[b * 2 * d + d + lane] * expf(0.5f * my_lv);
+        xt_s[i] = x;
+        const float dxv = x - xu_s[b * du + lane];
+        dx_s[i] = dxv;
+        sc[SC_SDX] = fmaf(dxv, dxv, sc[SC_SDX]);
+        // posterior of this step -> trajectory (returned by filter / fit, model.py:218-221, :305-307)
+        p.mu[((size_t)t * p.B + b0 + b) * d + lane] = my_m;
+        p.logvar[((size_t)t * p.B + b0 + b) * d + lane] = my_lv;
+      }
+    }
+    __syncthreads();
+
+    VJF_STAMP(p, t, 13);
+    // ---- S5/S6: decoder eta = D xt + bias (model.py:29-30), likelihood terms, dloss/deta (times B), g_xt = g_eta D,
+    //      decoder gradients.  Specialised on the state dimension so that xt and the accumulators live in registers.
+    switch (d) {
+      case 1: decoder_stage<1>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+      case 2: decoder_stage<2>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+      case 3: decoder_stage<3>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+      case 4: decoder_stage<4>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+      default: if (d <= 8) decoder_stage<8>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
+               else decoder_stage<16>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
+    }
+
+    VJF_STAMP(p, t, 18);
+    // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
+    mma_gram(phi_s, Rp, R, rows, slot + p.pa, first);
+    {
+      float* bp = slot + p.pb;
+      for (int i = tid; i < R * d; i += VJF_NT) {
+        const int r = i / d, k = i - r * d;
+        float s = 0.f;
+        for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r], dx_s[b * d + k], s);
+        acc_store(bp + i, s, first);
+      }
+    }
+    VJF_STAMP(p, t, 19);
+    if (part == PART_FRONT) {
+      // park the scalar sums of the front half until the back half finishes the tile
+#pragma unroll
+      for (int i = 0; i < VJF_NSCAL; ++i) {
+        const float s = warp_sum(sc[i]);
+        if (lane == 0) red_s[warp * VJF_NSCAL + i] = s;
+      }
+      __syncthreads();
+      if (tid < VJF_NSCAL) {
+        float s = 0.f;
+        for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
+        scf_s[tid] = s;
+      }
+      __syncthreads();
+      return;
+    }
+    __syncthreads();
+  }
+
+  // =============================== back half ===============================
+  const float gam = st[p.lay.tr_logvar];
+  const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
+  if (part == PART_BACK) {
+    cp_async_wait_all();  // w_chol / w_mean staged by the back prologue
+    __syncthreads();
+  }
   VJF_STAMP(p, t, 10);
+  if (first && p.U_in_smem) {  // is w_chol upper triangular?  (lets the quadratic form skip the zero blocks)
+    const float* U_s = sm + p.s_U;
+    int nz = 0;
+    for (int r = warp; r < R; r += VJF_NWARP)
+      for (int c = lane; c < r; c += 32) nz |= (U_s[r * p.ldu + c] != 0.f);
+    nz = __syncthreads_or(nz);
+    if (tid == 0) *flag_s = nz;
+    __syncthreads();
+  }
   // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
   //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
   if (p.U_in_smem) {
@@ -320,69 +426,12 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       if (lane == 0) pm_s[b * d + k] = xu_s[b * du + k] + s;
     }
   }
-
-  VJF_STAMP(p, t, 11);
-  // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
-  const float* hL; int ldh, HL;
-  {
-    const float* A = in_s; int lda = K1p, K = K1;
-    for (int l = 0; l < L; ++l) {
-      float* out = sm + p.s_act[l];
-      const bool w_sm = (l == 0) && p.W1_in_smem;
-      mma_linear_fwd(A, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
-                     p.Hp[l], rows, true);
-      // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
-      const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
-      if (h16 > h8)
-        for (int i = tid; i < rows * (h16 - h8); i += VJF_NT) out[(i / (h16 - h8)) * p.Hp[l] + h8 + i % (h16 - h8)] = 0.f;
-      __syncthreads();
-      A = out; lda = p.Hp[l]; K = p.H[l];
-    }
-    hL = A; ldh = lda; HL = K;
-  }
-  VJF_STAMP(p, t, 12);
-  // p_logvar from the n-tile partial sums (qp_s complete after the barrier above)
+  __syncthreads();
+  // p_logvar from the n-tile partial sums
   if (tid < nb) {
     float q = qp_s[tid];
     if (p.U_in_smem) { const int nt = (R + 7) >> 3; for (int n = 1; n < nt; ++n) q += qp_s[n * rows + tid]; }
     plv_s[tid] = logf(q);
-  }
-  // heads: m_t = W_m h (no bias), l_t = W_v h + b_v ; then xt = m_t + eps2 exp(l_t/2), dx = xt - xs
-  for (int b = warp; b < nb; b += VJF_NWARP) {
-    float my_m = 0.f, my_lv = 0.f;
-    for (int k = 0; k < d; ++k) {
-      float m = 0.f, lv = 0.f;
-      const float* wm = hm_s + k;
-      const float* wv = hv_s + k;
-      for (int n = lane; n < HL; n += 32) { const float h = hL[b * ldh + n]; m = fmaf(h, wm[n * d], m); lv = fmaf(h, wv[n * d], lv); }
-      m = warp_sum(m); lv = warp_sum(lv);
-      if (lane == k) { my_m = m; my_lv = lv + hv_s[HL * d + k]; }
-    }
-    if (lane < d) {
-      const int i = b * d + lane;
-      mt_s[i] = my_m; lt_s[i] = my_lv;
-      const float x = my_m + eps_s[b * 2 * d + d + lane] * expf(0.5f * my_lv);
-      xt_s[i] = x;
-      const float dxv = x - xu_s[b * du + lane];
-      dx_s[i] = dxv;
-      sc[SC_SDX] = fmaf(dxv, dxv, sc[SC_SDX]);
-      // posterior of this step -> trajectory (returned by filter / fit, model.py:218-221, :305-307)
-      p.mu[((size_t)t * p.B + b0 + b) * d + lane] = my_m;
-      p.logvar[((size_t)t * p.B + b0 + b) * d + lane] = my_lv;
-    }
-  }
-  __syncthreads();
-
-  VJF_STAMP(p, t, 13);
-  // ---- S5/S6: decoder eta = D xt + bias (model.py:29-30), likelihood terms, dloss/deta (times B), g_xt = g_eta D,
-  //      decoder gradients.  Specialised on the state dimension so that xt and the accumulators live in registers.
-  switch (d) {
-    case 1: decoder_stage<1>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
-    case 2: decoder_stage<2>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
-    case 3: decoder_stage<3>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
-    case 4: decoder_stage<4>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
-    default: if (d <= 8) decoder_stage<8>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
-             else decoder_stage<16>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
   }
   __syncthreads();
 
@@ -423,15 +472,13 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       acc_store(slot + p.lay.head_v_b + lane, s, first);
     }
     // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2); pad columns up to a multiple of 8 are zero
-    const float* wm = hm_s;
-    const float* wv = hv_s;
     const int H8 = (HL + 7) & ~7;
     for (int b = warp; b < nb; b += VJF_NWARP) {
       for (int n = lane; n < H8; n += 32) {
         float v = 0.f;
         if (n < HL) {
           float s = 0.f;
-          for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], wm[n * d + k], s); s = fmaf(glt_s[b * d + k], wv[n * d + k], s); }
+          for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], hm_s[n * d + k], s); s = fmaf(glt_s[b * d + k], hv_s[n * d + k], s); }
           const float h = hL[b * ldh + n];
           v = s * (1.0f - h * h);
         }
@@ -468,20 +515,6 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     }
   }
 
-  VJF_STAMP(p, t, 18);
-  // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
-  mma_gram(phi_s, Rp, R, rows, slot + p.pa, first);
-  {
-    float* bp = slot + p.pb;
-    for (int i = tid; i < R * d; i += VJF_NT) {
-      const int r = i / d, k = i - r * d;
-      float s = 0.f;
-      for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r], dx_s[b * d + k], s);
-      acc_store(bp + i, s, first);
-    }
-  }
-
-  VJF_STAMP(p, t, 19);
   // ---- scalar sums of the tile ----
 #pragma unroll
   for (int i = 0; i < VJF_NSCAL; ++i) {
@@ -490,7 +523,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   }
   __syncthreads();
   if (tid < VJF_NSCAL) {
-    float s = 0.f;
+    float s = (part == PART_BACK) ? scf_s[tid] : 0.f;
     for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
     if (tid == 6) acc_store(slot + p.lay.lik_logvar, s, first);  // Gaussian d loss / d lambda (times B)
     else acc_store(slot + p.ps + tid, s, first);
@@ -499,42 +532,49 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   VJF_STAMP(p, t, 20);
 }
 
-// Start the asynchronous staging (cp.async) of every parameter the tiles of this step share; the first tile
-// waits for it after it has issued its own observation loads, so the two overlap.
-static __device__ void phase_a_prologue(const StepParams& p, float* sm) {
+// Asynchronous staging (cp.async) of the parameters the tiles of a step share.  STAGE_FRONT: what the front
+// half reads (RBF centres/widths, recognition layer-1 weight, head weights, decoder) -- final once the SGD
+// step of the previous time step is done.  STAGE_BACK: w_mean / w_chol -- final once its RLS is done.
+#define STAGE_FRONT 1
+#define STAGE_BACK 2
+static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what) {
   const int tid = threadIdx.x;
   const float* st = p.state;
   const int HL = p.H[p.L - 1];
-  stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
-  stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
-  stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
-  stage_async(sm + p.s_hm, p.d, st + p.lay.head_m_w, p.d, HL, p.d, tid, VJF_NT);
-  stage_async(sm + p.s_hv, p.d, st + p.lay.head_v_w, p.d, HL, p.d, tid, VJF_NT);
-  stage_async(sm + p.s_hv + HL * p.d, p.d, st + p.lay.head_v_b, p.d, 1, p.d, tid, VJF_NT);
-  if (p.dec_in_smem) {
-    stage_async(sm + p.s_dec, p.D, st + p.lay.dec_w, p.D, p.d, p.D, tid, VJF_NT);
-    stage_async(sm + p.s_dec + p.d * p.D, p.D, st + p.lay.dec_b, p.D, 1, p.D, tid, VJF_NT);
+  if (what & STAGE_FRONT) {
+    stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
+    stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
+    stage_async(sm + p.s_hm, p.d, st + p.lay.head_m_w, p.d, HL, p.d, tid, VJF_NT);
+    stage_async(sm + p.s_hv, p.d, st + p.lay.head_v_w, p.d, HL, p.d, tid, VJF_NT);
+    stage_async(sm + p.s_hv + HL * p.d, p.d, st + p.lay.head_v_b, p.d, 1, p.d, tid, VJF_NT);
+    if (p.dec_in_smem) {
+      stage_async(sm + p.s_dec, p.D, st + p.lay.dec_w, p.D, p.d, p.D, tid, VJF_NT);
+      stage_async(sm + p.s_dec + p.d * p.D, p.D, st + p.lay.dec_b, p.D, 1, p.D, tid, VJF_NT);
+    }
+    if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
   }
-  if (p.U_in_smem) {
-    float* U_s = sm + p.s_U;
-    const int Rk = (p.R + 7) & ~7, ldu = p.ldu;
-    stage_async(U_s, ldu, st + p.lay.w_chol, p.R, p.R, p.R, tid, VJF_NT);
-    // zero padding (disjoint from the async destinations)
-    for (int i = tid; i < Rk * ldu; i += VJF_NT) { const int r = i / ldu, c = i - r * ldu; if (r >= p.R || c >= p.R) U_s[i] = 0.f; }
+  if (what & STAGE_BACK) {
+    stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
+    if (p.U_in_smem) {
+      float* U_s = sm + p.s_U;
+      const int Rk = (p.R + 7) & ~7, ldu = p.ldu;
+      stage_async(U_s, ldu, st + p.lay.w_chol, p.R, p.R, p.R, tid, VJF_NT);
+      // zero padding (disjoint from the async destinations)
+      for (int i = tid; i < Rk * ldu; i += VJF_NT) { const int r = i / ldu, c = i - r * ldu; if (r >= p.R || c >= p.R) U_s[i] = 0.f; }
+    }
   }
-  if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
   cp_async_commit();
-  if (tid == 0) *reinterpret_cast<int*>(sm + p.s_flag) = 0;
 }
 
+// whole phase A for the non-overlapped schedule (also the split multi-GPU path): every CTA walks its tiles
 static __device__ void phase_a(const StepParams& p, float* sm, int t, unsigned masks) {
   VJF_STAMP(p, t, 7);
   __syncthreads();  // the previous phase is done with the shared memory that is re-planned here
-  phase_a_prologue(p, sm);
+  phase_a_prologue(p, sm, STAGE_FRONT | STAGE_BACK);
   VJF_STAMP(p, t, 21);
   bool first = true;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    phase_a_tile(p, sm, t, tile, first, masks);
+    phase_a_tile(p, sm, t, tile, first, masks, PART_BOTH);
     first = false;
   }
   if (first) {  // a CTA without tiles still owns a slot: zero it
@@ -569,7 +609,7 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
     return;
   }
   const int el = tid & 127, cg = tid >> 7;  // 128 elements x 4 slot groups per CTA pass
-  float* red4 = sm;                          // [4][128]
+  float* red4 = sm + p.s_b1;                 // [4][128], outside the phase-A arrays (overlapped schedule)
   const int per = (nslots + 3) >> 2;
   const int c0 = cg * per, c1 = min(nslots, c0 + per);
   for (int base = p.red_begin + cta * 128; base < p.PS; base += nctas * 128) {
@@ -635,69 +675,114 @@ static __device__ double block_sum_d(double v, double* red) {
 // 1/sqrt(pivot_k) the three row groups hold chol(P'), (L^-1 g)^T and L^-T = w_chol.  Row r lives in warp
 // r % 16 (register slot r / 16), column j in lane j % 32 (slot j / 32): the sweep touches shared memory only
 // to broadcast the current column.  Returns false (block-uniform) if a pivot is not positive.
-template <int CPL, int RPW>
-static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv, int t) {
+// One range [k0, k1) of the LDL^T sweep with compile-time register slots: CN = slot of column k, CNP = slot of
+// column k + 1.  Multipliers of a warp's own rows come from a warp shuffle (element (r, k) lives in lane k % 32 of
+// the warp that owns row r); only the P'-rows' entries of the next column travel through shared memory.
+template <int CPL, int RPW, int PR, int NW, int CN, int CNP>
+__device__ __forceinline__ bool ldl_sweep_range(float (&v)[RPW][CPL], const int (&jj)[CPL], float* colbuf, float* dvec, int k0, int k1,
+                                                int R, int& kb) {
+  constexpr int NRP = NW * RPW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = k0; k < k1; ++k) {
+    const float* cb = colbuf + kb * NRP;
+    float* cbn = colbuf + (kb ^ 1) * NRP;
+    const float piv = cb[k];
+    float tk[RPW], cj[CPL];
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) { const float x = cb[lane + 32 * ci]; cj[ci] = (jj[ci] > k) ? x : 0.f; }
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) tk[ri] = __shfl_sync(0xffffffffu, v[ri][CN], k & 31);
+    if (!(piv > 0.f)) return false;
+    float rinv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(piv));
+    rinv = fmaf(rinv, fmaf(-piv, rinv, 1.0f), rinv);  // one Newton step: < 1 ulp
+    if (threadIdx.x == 0) dvec[k] = piv;
+    const float ninv = -rinv;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) tk[ri] *= ninv;
+#pragma unroll
+    for (int ri = 0; ri < RPW; ++ri) {
+#pragma unroll
+      for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = fmaf(tk[ri], cj[ci], v[ri][ci]);
+    }
+    if (lane == ((k + 1) & 31)) {
+#pragma unroll
+      for (int ri = 0; ri < PR; ++ri) cbn[warp + NW * ri] = v[ri][CNP];  // rows >= R in these slots are never read
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");  // only the sweep warps
+    kb ^= 1;
+  }
+  return true;
+}
+
+template <int CPL, int RPW, int NW>
+static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv, int t,
+                                       double* resid_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, d = p.d, NR = 2 * R + d;
-  constexpr int NRP = VJF_NWARP * RPW;          // rows incl. padding: every (warp, slot) pair is a row
+  // NW warps take part (row r lives in warp r % NW)
+  constexpr int NRP = NW * RPW;                 // rows incl. padding: every (warp, slot) pair is a row
+  constexpr int PR = (RPW + 1) / 2;             // register slots that can hold P rows (R <= NR / 2)
+  const bool active_warp = warp < NW;
+  const int ldq = R | 1;                        // odd row stride: conflict-free column walks
   float* colbuf = sm;                           // [2][NRP]
   float* dvec = colbuf + 2 * NRP;               // [R]
   float* zbuf = dvec + ((R + 3) & ~3);          // [d][R]   g, later z = L^-1 g
-  float* Ws = zbuf + ((d * R + 3) & ~3);        // [R][d]   old W staged
+  float* Ws = zbuf + ((d * R + 3) & ~3);        // [R][d]   old W, later W'
   float* bs = Ws + ((d * R + 3) & ~3);          // [R][d]   b staged
-  float* misc = bs + ((d * R + 3) & ~3);        // [0..1] 1/pivot (double buffered), [2] fail flag
+  float* misc = bs + ((d * R + 3) & ~3);        // [0] fail flag
+  double* dred = reinterpret_cast<double*>(misc + 4);  // [NWARP] (8-byte aligned: all sizes above are multiples of 4 floats)
+  float* Qs = misc + 4 + 2 * VJF_NWARP + 4;     // [R][ldq]  P (for g = P W), later w_chol (for W' = w_chol z)
   float* st = p.state;
   const float* P = st + p.lay.w_precision;
   float v[RPW][CPL];
-  float v0[(RPW + 1) / 2][CPL];                 // P' rows kept for the commit (P rows occupy the first slots)
-  const int rpw_used = (NR + VJF_NWARP - 1) / VJF_NWARP;
+  float v0[PR][CPL];                            // P' rows kept for the commit
+  float a_in[PR][CPL];                          // lower triangle of A (kept for the residual at the end)
   // ---- issue every global load first (P rows, A rows, W, b), then compute ----
-  float a_in[(RPW + 1) / 2][CPL];
 #pragma unroll
-  for (int ri = 0; ri < (RPW + 1) / 2; ++ri) {
-    const int r = warp + VJF_NWARP * ri;
+  for (int ri = 0; ri < PR; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) {
       const int j = lane + 32 * ci;
       const bool ok = (r < R) && (j < R);
       v[ri][ci] = ok ? P[r * R + j] : 0.f;
-      a_in[ri][ci] = (ok && j <= r) ? A[r * R + j] : 0.f;  // lower triangle of the symmetric A
+      a_in[ri][ci] = (ok && j <= r) ? A[r * R + j] : 0.f;
     }
   }
   for (int i = tid; i < R * d; i += VJF_NT) { Ws[i] = st[p.lay.w_mean + i]; bs[i] = bv[i]; }
-  if (tid == 0) misc[2] = 0.f;
-  __syncthreads();
 #pragma unroll
-  for (int ri = 0; ri < (RPW + 1) / 2; ++ri) {
-    const int r = warp + VJF_NWARP * ri;
-    if (r < R) {
-      // g[r][c] = sum_j P[r][j] W[j][c] + b[r][c]/v   (old P, old W: module.py:93)
-      for (int c = 0; c < d; ++c) {
-        float s = 0.f;
+  for (int ri = 0; ri < PR; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
 #pragma unroll
-        for (int ci = 0; ci < CPL; ++ci) {
-          const int j = lane + 32 * ci;
-          if (j < R) s = fmaf(v[ri][ci], Ws[j * d + c], s);
-        }
-        s = warp_sum(s);
-        if (lane == 0) zbuf[c * R + r] = fmaf(bs[r * d + c], iv, s);
-      }
-#pragma unroll
-      for (int ci = 0; ci < CPL; ++ci) {
-        v[ri][ci] = fmaf(a_in[ri][ci], iv, v[ri][ci]);   // P' = P + A/v on and below the diagonal
-        v0[ri][ci] = v[ri][ci];
-      }
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      if (r < R && j < R) Qs[r * ldq + j] = v[ri][ci];
+      v[ri][ci] = fmaf(a_in[ri][ci], iv, v[ri][ci]);   // P' = P + A/v on and below the diagonal
+      v0[ri][ci] = v[ri][ci];
     }
   }
 #pragma unroll
-  for (int ri = (RPW + 1) / 2; ri < RPW; ++ri)
+  for (int ri = PR; ri < RPW; ++ri)
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = 0.f;
+  if (tid == 0) misc[0] = 0.f;
+  __syncthreads();
+  // g[r][c] = sum_j P[r][j] W[j][c] + b[r][c]/v   (old P, old W: module.py:93); one thread per output
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int r = i / d, c = i - r * d;
+    float s0 = 0.f, s1 = 0.f;
+    const float* q = Qs + r * ldq;
+    int j = 0;
+    for (; j + 1 < R; j += 2) { s0 = fmaf(q[j], Ws[j * d + c], s0); s1 = fmaf(q[j + 1], Ws[(j + 1) * d + c], s1); }
+    if (j < R) s0 = fmaf(q[j], Ws[j * d + c], s0);
+    zbuf[c * R + r] = fmaf(bs[i], iv, s0 + s1);
+  }
   VJF_STAMP(p, t, 25);
   __syncthreads();
 #pragma unroll
   for (int ri = 0; ri < RPW; ++ri) {
-    const int r = warp + VJF_NWARP * ri;
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
     if (r >= R) {
 #pragma unroll
       for (int ci = 0; ci < CPL; ++ci) {
@@ -709,111 +794,110 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
       }
     }
   }
-  // publish column 0 and 1/pivot_0
-  if (lane == 0) {
+  // publish column 0
+  if (lane == 0 && active_warp) {
 #pragma unroll
-    for (int ri = 0; ri < RPW; ++ri) colbuf[warp + VJF_NWARP * ri] = v[ri][0];
-    if (warp == 0) { const float pv = v[0][0]; misc[0] = 1.0f / pv; if (!(pv > 0.f)) misc[2] = 1.f; }
+    for (int ri = 0; ri < RPW; ++ri) colbuf[warp + NW * ri] = v[ri][0];
   }
+  int jj[CPL];  // column index of each slot, -1 when it is not a column of P'
+#pragma unroll
+  for (int ci = 0; ci < CPL; ++ci) { const int j = lane + 32 * ci; jj[ci] = (j < R) ? j : -1; }
   __syncthreads();
   VJF_STAMP(p, t, 26);
   // ---- the sweep.  No row predicates are needed: rows above the pivot only touch their (unused) upper
-  //      triangle, and an identity row whose column has not been reached has a zero multiplier. ----
+  //      triangle, and an identity row whose column has not been reached has a zero multiplier.  Every
+  //      thread forms 1/pivot itself from the broadcast column, so the only cross-warp traffic per column
+  //      is the publication of the next column. ----
   int kb = 0;
   bool fail = false;
-  for (int k = 0; k < R; ++k) {
-    const float* cb = colbuf + kb * NRP;
-    float* cbn = colbuf + (kb ^ 1) * NRP;
-    if (misc[2] != 0.f) { fail = true; break; }
-    const float inv = misc[kb];
-    if (tid == 0) dvec[k] = cb[k];
-    float cj[CPL];
-#pragma unroll
-    for (int ci = 0; ci < CPL; ++ci) { const int j = lane + 32 * ci; cj[ci] = (j > k && j < R) ? cb[j] : 0.f; }
-#pragma unroll
-    for (int ri = 0; ri < RPW; ++ri) {
-      if (ri < rpw_used) {
-        const float tk = cb[warp + VJF_NWARP * ri] * inv;
-#pragma unroll
-        for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = fmaf(-tk, cj[ci], v[ri][ci]);
-      }
+  if (active_warp) {
+    bool ok = true;
+    if (CPL == 2) {
+      ok = ldl_sweep_range<CPL, RPW, PR, NW, 0, 0>(v, jj, colbuf, dvec, 0, min(R, 31), R, kb);
+      if (ok && R > 31) ok = ldl_sweep_range<CPL, RPW, PR, NW, 0, (CPL > 1 ? 1 : 0)>(v, jj, colbuf, dvec, 31, 32, R, kb);
+      if (ok && R > 32) ok = ldl_sweep_range<CPL, RPW, PR, NW, (CPL > 1 ? 1 : 0), (CPL > 1 ? 1 : 0)>(v, jj, colbuf, dvec, 32, R, R, kb);
+    } else {
+#define VJF_SW(CNv, CNPv, a, b) if (ok && R > (a)) ok = ldl_sweep_range<CPL, RPW, PR, NW, (CNv) < CPL ? (CNv) : 0, (CNPv) < CPL ? (CNPv) : 0>(v, jj, colbuf, dvec, (a), min(R, (b)), R, kb);
+      VJF_SW(0, 0, 0, 31) VJF_SW(0, 1, 31, 32) VJF_SW(1, 1, 32, 63) VJF_SW(1, 2, 63, 64)
+      VJF_SW(2, 2, 64, 95) VJF_SW(2, 3, 95, 96) VJF_SW(3, 3, 96, 128)
+#undef VJF_SW
     }
-    const int kn = k + 1;
-    if (kn < R && lane == (kn & 31)) {
-      const int cn = kn >> 5;
-#pragma unroll
-      for (int ri = 0; ri < RPW; ++ri) {
-        float x = v[ri][0];
-#pragma unroll
-        for (int ci = 1; ci < CPL; ++ci) x = (cn == ci) ? v[ri][ci] : x;
-        cbn[warp + VJF_NWARP * ri] = x;
-      }
-      if (warp == (kn & (VJF_NWARP - 1))) {
-        const float x = cbn[kn];
-        misc[kb ^ 1] = 1.0f / x;
-        if (!(x > 0.f)) misc[2] = 1.f;
-      }
-    }
-    __syncthreads();
-    kb ^= 1;
+    fail = !ok;
+    if (tid == 0) misc[0] = fail ? 1.f : 0.f;
   }
-  if (!fail && misc[2] != 0.f) fail = true;
+  __syncthreads();
+  fail = misc[0] != 0.f;
   VJF_STAMP(p, t, 27);
   if (fail) return false;
-  __syncthreads();
   // ---- scale the columns and commit: w_pchol = L, w_chol = L^-T, z ; then W' = w_chol z ----
   float* Lout = st + p.lay.w_pchol;
   float* Uout = st + p.lay.w_chol;
   float* Pout = st + p.lay.w_precision;
-  float sdv[CPL];
+  float sdv[CPL], isd[CPL];
 #pragma unroll
   for (int ci = 0; ci < CPL; ++ci) {
     const int j = lane + 32 * ci;
     sdv[ci] = (j < R) ? sqrtf(dvec[j]) : 1.f;
+    isd[ci] = 1.0f / sdv[ci];
   }
 #pragma unroll
   for (int ri = 0; ri < RPW; ++ri) {
-    const int r = warp + VJF_NWARP * ri;
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
     if (r >= NR) continue;
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) {
       const int j = lane + 32 * ci;
       if (j >= R) continue;
-      const float x = v[ri][ci] / sdv[ci];
+      const float x = v[ri][ci] * isd[ci];
       if (r < R) {
         Lout[r * R + j] = (j < r) ? x : ((j == r) ? sdv[ci] : 0.f);
-        if (ri < (RPW + 1) / 2 && j <= r) { Pout[r * R + j] = v0[ri][ci]; Pout[j * R + r] = v0[ri][ci]; }
+        if (ri < PR && j <= r) { Pout[r * R + j] = v0[ri][ci]; Pout[j * R + r] = v0[ri][ci]; }
       } else if (r < R + d) {
         zbuf[(r - R) * R + j] = x;
       } else {
         const int c = r - R - d;
         const float uv = (j >= c) ? x : 0.f;
         Uout[c * R + j] = uv;
-        v[ri][ci] = uv;
+        Qs[c * ldq + j] = uv;
       }
     }
   }
   __syncthreads();
   VJF_STAMP(p, t, 28);
+  // W'[c][i] = sum_{j >= c} w_chol[c][j] z[i][j] ; one thread per output
   float* Wout = st + p.lay.w_mean;
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int c = i / d, k = i - c * d;
+    float s0 = 0.f, s1 = 0.f;
+    const float* q = Qs + c * ldq;
+    const float* z = zbuf + k * R;
+    int j = c;
+    for (; j + 1 < R; j += 2) { s0 = fmaf(q[j], z[j], s0); s1 = fmaf(q[j + 1], z[j + 1], s1); }
+    if (j < R) s0 = fmaf(q[j], z[j], s0);
+    const float w = s0 + s1;
+    Wout[i] = w; Ws[i] = w;
+  }
+  __syncthreads();
+  VJF_STAMP(p, t, 29);
+  // ---- sum |dx - phi W'|^2 - S = <W', A W'> - 2 <W', b> from the statistics still in registers / shared memory ----
+  double acc = 0.0;
 #pragma unroll
-  for (int ri = 0; ri < RPW; ++ri) {
-    const int r = warp + VJF_NWARP * ri;
-    if (r >= R + d && r < NR) {
-      const int c = r - R - d;
-      for (int i = 0; i < d; ++i) {
-        float s = 0.f;
+  for (int ri = 0; ri < PR; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
+    if (r < R) {
 #pragma unroll
-        for (int ci = 0; ci < CPL; ++ci) {
-          const int j = lane + 32 * ci;
-          if (j < R) s = fmaf(v[ri][ci], zbuf[i * R + j], s);
+      for (int ci = 0; ci < CPL; ++ci) {
+        const int j = lane + 32 * ci;
+        if (j <= r) {  // lower triangle of the symmetric A, off-diagonal counted twice
+          float w2 = 0.f;
+          for (int k = 0; k < d; ++k) w2 = fmaf(Ws[r * d + k], Ws[j * d + k], w2);
+          acc += (double)((j < r ? 2.0f : 1.0f) * a_in[ri][ci]) * (double)w2;
         }
-        s = warp_sum(s);
-        if (lane == 0) { Wout[c * d + i] = s; Ws[c * d + i] = s; }
       }
     }
   }
-  __syncthreads();
+  for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)Ws[i] * (double)bs[i];
+  *resid_out = block_sum_d(acc, dred);
   return true;
 }
 
@@ -937,19 +1021,30 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   // mean squared increment (model.py:384-385)
   const float iv = p.init_mode ? (Bf * (float)d) / scal[SC_SDX] : 1.0f / expf(gam);
   __syncthreads();
+  bool have_resid = false;
+  double resid = 0.0;
   if (!warm) {
     bool ok;
-    if (R <= 64) ok = rls_factor_regs<2, 9>(p, sm, iv, A, bv, t);
-    else if (R <= 128) ok = rls_factor_regs<4, 17>(p, sm, iv, A, bv, t);
+    const int nr16 = (2 * R + d + VJF_NWARP - 1) / VJF_NWARP;  // rows per warp of the work matrix
+    const int nr8 = (2 * R + d + 7) / 8;  // rows per warp with 8 sweep warps
+    (void)nr16;
+    (void)nr8;
+    if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
+    else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
+    else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
+    else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
+    else if (R <= 128) { ok = rls_factor_regs<4, 17, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
     else ok = rls_factor_smem(p, sm, iv, A, bv);
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
   }
-  VJF_STAMP(p, t, 29);
 
   // ---- state-noise running variance (vjf/model.py:373-377).  sum |dx - phi W'|^2 from the reduced
   //      statistics: S - 2 <W', b> + <W', A W'>, evaluated in double ----
-  {
+  double tot;
+  if (have_resid) {
+    tot = resid + (double)scal[SC_SDX];
+  } else {
     float* wbuf = sm;                                      // [R][d] current W
     const size_t doff = ((size_t)R * d + 5) & ~(size_t)1;  // 8-byte aligned
     double* dred = reinterpret_cast<double*>(sm + doff);   // [NWARP]
@@ -964,7 +1059,9 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
       }
     }
     for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)wbuf[i] * (double)bv[i];
-    const double tot = block_sum_d(acc, dred) + (double)scal[SC_SDX];
+    tot = block_sum_d(acc, dred) + (double)scal[SC_SDX];
+  }
+  {
     if (tid == 0) {
       const float mse = (float)(fmax(tot, 0.0) / ((double)p.Bglobal * (double)d));
       if (p.init_mode) { st[p.lay.tr_logvar] = logf(mse); return; }  // model.py:387-388
@@ -979,7 +1076,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
 // finite flags of the three ELBO terms from the slots (every CTA evaluates this identically)
 static __device__ unsigned term_finite_mask(const StepParams& p, const float* src, int nslots, float* sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned* flag = reinterpret_cast<unsigned*>(sm);
+  unsigned* flag = reinterpret_cast<unsigned*>(sm + p.s_b1);
   if (warp == 0) {
     unsigned m = 0;
     for (int i = 0; i < 3; ++i) {
