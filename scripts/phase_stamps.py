@@ -41,3 +41,13 @@ b2 = [(4, 24, "losses/lik"), (24, 25, "load P,A,W,b + g"), (25, 26, "rows init+p
 print(" phase B2 stages (CTA 0):")
 for i, j, n in b2:
     print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
+
+dc = (s[-1, 40] - s[4, 40]).item(); dg = (s[-1, 0] - s[4, 0]).item()
+print(f" effective SM clock of CTA 0 during the run: {dc / dg * 1e3:.0f} MHz (clock64 ticks / globaltimer ns)")
+
+import numpy as np
+tk = (C.c_longlong * 160)()
+lib.vjf_debug_read_sweep.argtypes = [C.c_void_p]; lib.vjf_debug_read_sweep.restype = C.c_int
+lib.vjf_debug_read_sweep(tk)
+tk = np.array(tk[:R], dtype=np.int64)
+print(" sweep: cycles per column (clock64, last step):", np.diff(tk).tolist())

@@ -37,7 +37,7 @@ struct StepParams {
   int TB, ntiles, nslots;
   // ---- shared-memory plan (float offsets) ----
   int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
-      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_scf, s_b1, s_total;
+      s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_scf, s_b1, s_inl, s_phil, s_gpal, s_gpbl, s_total;
   int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
@@ -91,15 +91,25 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
 
 // Grid-wide barrier for the persistent (cooperatively launched) kernel.  `target` is a per-thread
 // running count of expected arrivals; the counter is zeroed by the host before each launch.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned nparticipants = 0) {
   __syncthreads();
-  target += gridDim.x;
+  target += nparticipants ? nparticipants : gridDim.x;
   if (threadIdx.x == 0) {
     __threadfence();
     red_release_add_u32(counter, 1u);
     while (ld_acquire_u32(counter) < target) {
     }
     __threadfence();  // gpu-scope fence: also drops stale L1 lines before the CTA reads peers' data
+  }
+  __syncthreads();
+}
+
+// Block-wide wait until a monotonically increasing device counter reaches `want` (producer side: fence + atomicAdd).
+__device__ __forceinline__ void wait_counter(const unsigned* counter, unsigned want) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire_u32(counter) < want) {
+    }
+    __threadfence();
   }
   __syncthreads();
 }

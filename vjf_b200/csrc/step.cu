@@ -39,8 +39,10 @@ __device__ __forceinline__ unsigned base_masks(const StepParams& p) {
 // serial factorisation of step t.
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float sm[];
-  unsigned target = 0;
+  unsigned target = 0, target2 = 0;
   const bool trial_cta = blockIdx.x > 0;
+  const bool early_rls = p.overlap && p.lik == VJF_LIK_POISSON;
+  const unsigned n_stat_chunks = (unsigned)(((p.PS + 127) >> 7) - (p.pa >> 7));
   if (p.overlap) {
     if (!trial_cta) {
       float* slot = p.partials;  // CTA 0 owns no trials: its slot stays zero
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
   for (int t = 0; t < p.T; ++t) {
     unsigned masks = base_masks(p), fin;
     VJF_STAMP(p, t, 0);
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[t * 64 + 40] = clock64();
     for (int attempt = 0;; ++attempt) {
       if (!p.overlap) {
         phase_a(p, sm, t, masks);
@@ -78,15 +81,35 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       }
       break;
     }
-    phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x);
-    VJF_STAMP(p, t, 3);
-    grid_barrier(p.barrier, target);
-    VJF_STAMP(p, t, 4);
-    if (blockIdx.x == 0) {
-      phase_b2(p, sm, t, fin);
-    } else if (p.overlap && t + 1 < p.T) {
-      phase_a_prologue(p, sm, STAGE_FRONT);
-      phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+    if (early_rls) {
+      // Poisson likelihood + overlapped schedule: nothing in the RLS depends on the SGD step, so CTA 0 starts the
+      // factorisation as soon as the statistics chunks are reduced, while the trial CTAs finish the gradient
+      // reduction + SGD, synchronise among themselves and go on to the front half of step t+1.
+      if (trial_cta) {
+        phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x - 1, gridDim.x - 1, p.ctrl + 1);
+        VJF_STAMP(p, t, 3);
+        grid_barrier(p.ctrl + 2, target2, gridDim.x - 1);
+        if (t + 1 < p.T) {
+          phase_a_prologue(p, sm, STAGE_FRONT);
+          phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+        }
+      } else {
+        VJF_STAMP(p, t, 3);
+        wait_counter(p.ctrl + 1, n_stat_chunks * (unsigned)(t + 1));
+        VJF_STAMP(p, t, 4);
+        phase_b2(p, sm, t, fin);
+      }
+    } else {
+      phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x);
+      VJF_STAMP(p, t, 3);
+      grid_barrier(p.barrier, target);
+      VJF_STAMP(p, t, 4);
+      if (blockIdx.x == 0) {
+        phase_b2(p, sm, t, fin);
+      } else if (p.overlap && t + 1 < p.T) {
+        phase_a_prologue(p, sm, STAGE_FRONT);
+        phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+      }
     }
     VJF_STAMP(p, t, 5);
     grid_barrier(p.barrier, target);
@@ -190,11 +213,16 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   size_t off = 0;
   auto take = [&](size_t n) { size_t at = off; off = (off + n + 3) & ~(size_t)3; return (int)at; };
   p.s_in = take((size_t)rows * p.K1p);
+  p.s_inl = take((size_t)rows * p.K1p);
   p.s_g = take((size_t)((tb + 3) & ~3) * p.Dp);  // only real trials are read back
   p.s_phi = take((size_t)rows * p.Rp);
+  p.s_phil = take((size_t)rows * p.Rp);
   for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)rows * p.Hp[l]);
   p.s_gpa = take((size_t)rows * p.Gp);
-  p.s_gpb = take((size_t)rows * p.Gp);
+  p.s_gpal = take((size_t)rows * p.Gp);
+  // the second (ping-pong) pair is only needed to back-propagate through more than one hidden layer
+  p.s_gpb = (p.L > 1) ? take((size_t)rows * p.Gp) : p.s_gpa;
+  p.s_gpbl = (p.L > 1) ? take((size_t)rows * p.Gp) : p.s_gpal;
   p.s_eps = take((size_t)rows * 2 * p.d);
   p.s_xu = take((size_t)rows * p.du);
   p.s_xt = take((size_t)rows * p.d); p.s_mt = take((size_t)rows * p.d); p.s_lt = take((size_t)rows * p.d);
@@ -211,7 +239,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_hv = take((size_t)p.H[p.L - 1] * p.d + p.d);
   p.s_flag = take(4);
   p.s_scf = take(VJF_NSCAL);
-  p.s_b1 = take(512 + 8);
+  p.s_b1 = take(2048 + 8);
   p.s_W = take((size_t)p.R * p.d);
   p.s_c = take((size_t)p.R * p.du);
   p.s_iw = take((size_t)p.R);
@@ -281,6 +309,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaFuncSetAttribute(vjf_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   VJF_CUDA_OK(cudaFuncSetAttribute(vjf_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   VJF_CUDA_OK(cudaFuncSetAttribute(vjf_phase_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
+  VJF_CUDA_OK(cudaFuncSetAttribute(vjf_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   h->max_slots = h->num_sms;  // one persistent CTA per SM
 
   StepParams& p = h->base;
@@ -370,6 +399,7 @@ extern "C" int vjf_init_state(vjf_handle* h, void* stream) {
 // ------------------------------------------------------------------------------------------
 static int launch_persistent(vjf_handle* h, StepParams& p, cudaStream_t s) {
   VJF_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), s));
+  VJF_CUDA_OK(cudaMemsetAsync(p.ctrl, 0, 8 * sizeof(unsigned), s));
   void* args[] = {(void*)&p};
   VJF_CUDA_OK(cudaLaunchCooperativeKernel((void*)vjf_persistent_kernel, dim3(p.nslots), dim3(VJF_NT), args,
                                           (size_t)p.s_total * sizeof(float), s));
@@ -389,6 +419,7 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
 // development aid (not part of the public header): per-phase timestamps of CTA 0 for the next launches
 static long long* g_dbg_ptr = nullptr;
 extern "C" void vjf_debug_set_stamps(long long* dev_ptr) { g_dbg_ptr = dev_ptr; }
+extern "C" int vjf_debug_read_sweep(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, g_sweep_ticks, sizeof(long long) * 160); }
 
 extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32_t y_dtype, const float* u,
                        const float* q0_mean, const float* q0_logvar, const float* eps, uint64_t seed, uint64_t step0,
@@ -414,7 +445,7 @@ extern "C" int vjf_step(vjf_handle* h, int32_t B, const float* y, const float* u
 }
 
 int vjf_internal_reduce(const StepParams& p, cudaStream_t s) {
-  vjf_reduce_kernel<<<(p.PS - p.red_begin + 127) / 128, VJF_NT, 2048, s>>>(p);
+  vjf_reduce_kernel<<<(p.PS - p.red_begin + 127) / 128, VJF_NT, (size_t)(p.s_b1 + 2048 + 8) * sizeof(float), s>>>(p);
   ++g_vjf_launches;
   VJF_CUDA_OK(cudaGetLastError());
   return 0;

@@ -82,10 +82,10 @@ __device__ __forceinline__ void tile_wgrad(const float* A, int lda, int K, const
 }
 
 // db[n] (+)= sum_b G[b][n]
-__device__ __forceinline__ void tile_colsum(const float* G, int ldg, int N, int rows, float* db, bool first) {
+__device__ __forceinline__ void tile_colsum(const float* G, const float* Gl, int ldg, int N, int rows, float* db, bool first) {
   for (int n = threadIdx.x; n < N; n += VJF_NT) {
     float s = 0.f;
-    for (int b = 0; b < rows; ++b) s += G[b * ldg + n];
+    for (int b = 0; b < rows; ++b) s += G[b * ldg + n] + Gl[b * ldg + n];
     acc_store(db + n, s, first);
   }
 }
@@ -111,13 +111,14 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
 #pragma unroll
     for (int k = 0; k < DX; ++k) { xt[k] = (k < d) ? xt_s[b * d + k] : 0.f; gx[k] = 0.f; }
     const float* yb = in_s + b * K1p;
+    const float* ybl = sm + p.s_inl + b * K1p;
     float* gb = g_s + b * Dp;
     for (int j = lane; j < D; j += 32) {
       float w[DX];
       float eta = db[j];
 #pragma unroll
       for (int k = 0; k < DX; ++k) { w[k] = (DX == d || k < d) ? dw[k * D + j] : 0.f; eta = fmaf(w[k], xt[k], eta); }
-      const float yv = yb[j];
+      const float yv = yb[j] + ybl[j];  // the staged observations are a (hi, lo) pair
       float g;
       if (p.lik == VJF_LIK_GAUSSIAN) {
         // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
@@ -179,7 +180,7 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
 #define PART_BOTH 0
 #define PART_FRONT 1
 #define PART_BACK 2
-static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part) {
+static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
   const int K1 = p.K1, K1p = p.K1p, Rp = p.Rp, Gp = p.Gp;
@@ -187,6 +188,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   const int nb = min(p.TB, p.B - b0);
   const int rows = (nb + 15) & ~15;
   float* in_s = sm + p.s_in;   float* phi_s = sm + p.s_phi;
+  float* inl_s = sm + p.s_inl; float* phil_s = sm + p.s_phil;  // lo parts of the presplit (hi, lo) pairs
+  float* gpal = sm + p.s_gpal; float* gpbl = sm + p.s_gpbl;
   float* gpa = sm + p.s_gpa;   float* gpb = sm + p.s_gpb;   float* eps_s = sm + p.s_eps;
   float* xu_s = sm + p.s_xu;   float* xt_s = sm + p.s_xt;   float* mt_s = sm + p.s_mt;
   float* lt_s = sm + p.s_lt;   float* pm_s = sm + p.s_pm;   float* dx_s = sm + p.s_dx;
@@ -257,8 +260,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
         } else {
           // pad rows of everything that is summed over the rows of the tile
           for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
-          for (int j = lane; j < Rp; j += 32) phi_s[b * Rp + j] = 0.f;
-          for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; }
+          for (int j = lane; j < Rp; j += 32) { phi_s[b * Rp + j] = 0.f; phil_s[b * Rp + j] = 0.f; }
+          for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; gpal[b * Gp + j] = 0.f; gpbl[b * Gp + j] = 0.f; }
           for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
         }
       }
@@ -282,7 +285,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     __syncthreads();
 
     VJF_STAMP(p, t, 9);
-    // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) ----
+    // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22), stored as a (hi, lo) pair;
+    //      the staged input matrix is split in place the same way (its extras were consumed by S1) ----
     for (int b = warp; b < nb; b += VJF_NWARP) {
       for (int k = lane; k < Rp; k += 32) {
         float v = 0.f;
@@ -291,9 +295,13 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
           for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[k * du + c]; d2 = fmaf(df, df, d2); }
           v = expf(d2 * iw_s[k]);
         }
-        phi_s[b * Rp + k] = v;
+        const float h = tf32_hi(v);
+        phi_s[b * Rp + k] = h;
+        phil_s[b * Rp + k] = v - h;
       }
     }
+    presplit_inplace(in_s, inl_s, rows * K1p);
+    __syncthreads();
 
     VJF_STAMP(p, t, 11);
     // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
@@ -302,7 +310,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       for (int l = 0; l < L; ++l) {
         float* out = sm + p.s_act[l];
         const bool w_sm = (l == 0) && p.W1_in_smem;
-        mma_linear_fwd(A, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
+        mma_linear_fwd(A, (l == 0) ? inl_s : nullptr, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
                        p.Hp[l], rows, true);
         // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
         const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
@@ -353,13 +361,13 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
 
     VJF_STAMP(p, t, 18);
     // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
-    mma_gram(phi_s, Rp, R, rows, slot + p.pa, first);
+    mma_gram(phi_s, phil_s, Rp, R, rows, slot + p.pa, first);
     {
       float* bp = slot + p.pb;
       for (int i = tid; i < R * d; i += VJF_NT) {
         const int r = i / d, k = i - r * d;
         float s = 0.f;
-        for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r], dx_s[b * d + k], s);
+        for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r] + phil_s[b * Rp + r], dx_s[b * d + k], s);
         acc_store(bp + i, s, first);
       }
     }
@@ -391,7 +399,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
     __syncthreads();
   }
   VJF_STAMP(p, t, 10);
-  if (first && p.U_in_smem) {  // is w_chol upper triangular?  (lets the quadratic form skip the zero blocks)
+  if (first && p.U_in_smem && t == 0) {  // is w_chol upper triangular?  Checked once per launch: every later w_chol is
+                                           // the L^-T this kernel computed itself (or unchanged)
     const float* U_s = sm + p.s_U;
     int nz = 0;
     for (int r = warp; r < R; r += VJF_NWARP)
@@ -403,7 +412,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
   //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
   if (p.U_in_smem) {
-    mma_quadform(phi_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, *flag_s == 0);
+    mma_quadform(phi_s, phil_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, *flag_s == 0);
   } else {
     const float* U = st + p.lay.w_chol;
     for (int b = warp; b < nb; b += VJF_NWARP) {
@@ -411,7 +420,8 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
       for (int k = lane; k < R; k += 32) {
         float fl = 0.f;
         const float* ph = phi_s + b * Rp;
-        for (int j = 0; j < R; ++j) fl = fmaf(ph[j], U[j * R + k], fl);
+        const float* pl = phil_s + b * Rp;
+        for (int j = 0; j < R; ++j) fl = fmaf(ph[j] + pl[j], U[j * R + k], fl);
         q = fmaf(fl, fl, q);
       }
       q = warp_sum(q);
@@ -421,7 +431,7 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
   for (int b = warp; b < nb; b += VJF_NWARP) {
     for (int k = 0; k < d; ++k) {
       float s = 0.f;
-      for (int r = lane; r < R; r += 32) s = fmaf(phi_s[b * Rp + r], W_s[r * d + k], s);
+      for (int r = lane; r < R; r += 32) s = fmaf(phi_s[b * Rp + r] + phil_s[b * Rp + r], W_s[r * d + k], s);
       s = warp_sum(s);
       if (lane == 0) pm_s[b * d + k] = xu_s[b * du + k] + s;
     }
@@ -482,18 +492,20 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
           const float h = hL[b * ldh + n];
           v = s * (1.0f - h * h);
         }
-        gpa[b * Gp + n] = v;
+        const float vh = tf32_hi(v);
+        gpa[b * Gp + n] = vh;
+        gpal[b * Gp + n] = v - vh;
       }
     }
     __syncthreads();
     VJF_STAMP(p, t, 17);
-    float* gcur = gpa; float* gnext = gpb;
+    float* gcur = gpa; float* gnext = gpb; float* gcurl = gpal; float* gnextl = gpbl;
     for (int l = L - 1; l >= 0; --l) {
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
       const int ldp = (l == 0) ? K1p : p.Hp[l - 1];
       const int Kl = (l == 0) ? K1 : p.H[l - 1];
-      mma_wgrad(Aprev, ldp, Kl, gcur, Gp, p.H[l], rows, slot + p.lay.mlp_w[l], first);
-      tile_colsum(gcur, Gp, p.H[l], nb, slot + p.lay.mlp_b[l], first);
+      mma_wgrad(Aprev, (l == 0) ? inl_s : nullptr, ldp, Kl, gcur, gcurl, Gp, p.H[l], rows, slot + p.lay.mlp_w[l], first);
+      tile_colsum(gcur, gcurl, Gp, p.H[l], nb, slot + p.lay.mlp_b[l], first);
       if (l > 0) {
         const float* Wl = st + p.lay.mlp_w[l];  // [Kl][H_l]
         const int N = p.H[l], K8 = (Kl + 7) & ~7;
@@ -502,15 +514,18 @@ static __device__ void phase_a_tile(const StepParams& p, float* sm, int t, int t
             float v = 0.f;
             if (k < Kl) {
               float s = 0.f;
-              for (int n = 0; n < N; ++n) s = fmaf(gcur[b * Gp + n], Wl[k * N + n], s);
+              for (int n = 0; n < N; ++n) s = fmaf(gcur[b * Gp + n] + gcurl[b * Gp + n], Wl[k * N + n], s);
               const float h = Aprev[b * ldp + k];
               v = s * (1.0f - h * h);
             }
-            gnext[b * Gp + k] = v;
+            const float vh = tf32_hi(v);
+            gnext[b * Gp + k] = vh;
+            gnextl[b * Gp + k] = v - vh;
           }
         }
         __syncthreads();
         float* tmp = gcur; gcur = gnext; gnext = tmp;
+        tmp = gcurl; gcurl = gnextl; gnextl = tmp;
       }
     }
   }
@@ -595,45 +610,54 @@ __device__ __forceinline__ bool sgd_applies(const StepParams& p, int e) {
 }
 
 // reduce `src` ([nslots][PS]) into p.reduced; when apply is set also take the SGD step (vjf/model.py:210-211)
-static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas) {
-  const int tid = threadIdx.x;
+// Chunks of 128 consecutive elements (32 float4 columns).  A CTA pass reduces one chunk: warp w sums slots
+// w, w+16, ... with 128-bit loads (all of a warp's loads are in flight together), the 16 partial sums are
+// combined in a fixed order through shared memory, and warp 0 writes the result and takes the SGD step.
+// Chunks are walked from the END of the vector, so the RLS statistics and the loss sums (which live at the
+// end) are reduced first; when `signal` is given, every finished statistics chunk bumps it so that the RLS CTA
+// can start the factorisation without waiting for the gradient part.
+static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas,
+                                unsigned* signal = nullptr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float invB = 1.0f / (float)p.Bglobal;
-  if (nslots < 16) {
-    // few slots (small batches): one thread per element, slots summed in order
-    for (int e = p.red_begin + cta * VJF_NT + tid; e < p.PS; e += nctas * VJF_NT) {
-      float tot = 0.f;
-      for (int c = 0; c < nslots; ++c) tot += src[(size_t)c * p.PS + e];
-      p.reduced[e] = tot;
-      if (apply && sgd_applies(p, e)) p.state[e] -= p.lr * clip1(tot * invB);
-    }
-    return;
-  }
-  const int el = tid & 127, cg = tid >> 7;  // 128 elements x 4 slot groups per CTA pass
-  float* red4 = sm + p.s_b1;                 // [4][128], outside the phase-A arrays (overlapped schedule)
-  const int per = (nslots + 3) >> 2;
-  const int c0 = cg * per, c1 = min(nslots, c0 + per);
-  for (int base = p.red_begin + cta * 128; base < p.PS; base += nctas * 128) {
-    const int e = base + el;
-    float s = 0.f;
-    if (e < p.PS) {
-      const float* q = src + e;
-      int c = c0;
-      for (; c + 7 < c1; c += 8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = q[(size_t)(c + i) * p.PS];
-        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+  float4* red = reinterpret_cast<float4*>(sm + p.s_b1);  // [16][32] float4
+  const int c_lo = p.red_begin >> 7, nchunks = (p.PS + 127) >> 7;
+  const int stat_chunk0 = p.pa >> 7;  // chunks >= this one hold RLS statistics / loss sums
+  for (int ch = nchunks - 1 - cta; ch >= c_lo; ch -= nctas) {
+    const int e0 = (ch << 7) + (lane << 2);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e0 < p.PS) {
+      const float* q = src + e0;
+      int c = warp;
+      for (; c + 3 * VJF_NWARP < nslots; c += 4 * VJF_NWARP) {
+        const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
+        const float4 v1 = *reinterpret_cast<const float4*>(q + (size_t)(c + VJF_NWARP) * p.PS);
+        const float4 v2 = *reinterpret_cast<const float4*>(q + (size_t)(c + 2 * VJF_NWARP) * p.PS);
+        const float4 v3 = *reinterpret_cast<const float4*>(q + (size_t)(c + 3 * VJF_NWARP) * p.PS);
+        acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+        acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
       }
-      for (; c < c1; ++c) s += q[(size_t)c * p.PS];
+      for (; c < nslots; c += VJF_NWARP) {
+        const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      }
     }
-    red4[cg * 128 + el] = s;
+    red[warp * 32 + lane] = acc;
     __syncthreads();
-    if (cg == 0 && e < p.PS) {
-      const float tot = (red4[el] + red4[128 + el]) + (red4[256 + el] + red4[384 + el]);
-      p.reduced[e] = tot;
-      if (apply && sgd_applies(p, e)) p.state[e] -= p.lr * clip1(tot * invB);
+    if (warp == 0 && e0 < p.PS) {
+      float4 t = red[lane];
+#pragma unroll
+      for (int w = 1; w < VJF_NWARP; ++w) { const float4 v = red[w * 32 + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+      *reinterpret_cast<float4*>(p.reduced + e0) = t;
+      if (apply && e0 < p.lay.n_train) {
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (sgd_applies(p, e0 + i)) p.state[e0 + i] -= p.lr * clip1(tv[i] * invB);
+      }
     }
     __syncthreads();
+    if (signal && ch >= stat_chunk0 && tid == 0) { __threadfence(); atomicAdd(signal, 1u); }
   }
 }
 
@@ -675,6 +699,8 @@ static __device__ double block_sum_d(double v, double* red) {
 // 1/sqrt(pivot_k) the three row groups hold chol(P'), (L^-1 g)^T and L^-T = w_chol.  Row r lives in warp
 // r % 16 (register slot r / 16), column j in lane j % 32 (slot j / 32): the sweep touches shared memory only
 // to broadcast the current column.  Returns false (block-uniform) if a pivot is not positive.
+__device__ long long g_sweep_ticks[160];  // development aid: clock64 at every column of the last sweep
+
 // One range [k0, k1) of the LDL^T sweep with compile-time register slots: CN = slot of column k, CNP = slot of
 // column k + 1.  Multipliers of a warp's own rows come from a warp shuffle (element (r, k) lives in lane k % 32 of
 // the warp that owns row r); only the P'-rows' entries of the next column travel through shared memory.
@@ -686,6 +712,7 @@ __device__ __forceinline__ bool ldl_sweep_range(float (&v)[RPW][CPL], const int 
   for (int k = k0; k < k1; ++k) {
     const float* cb = colbuf + kb * NRP;
     float* cbn = colbuf + (kb ^ 1) * NRP;
+    if (threadIdx.x == 0) g_sweep_ticks[k] = clock64();
     const float piv = cb[k];
     float tk[RPW], cj[CPL];
 #pragma unroll
