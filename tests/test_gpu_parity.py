@@ -289,3 +289,15 @@ def test_initialize_and_forecast_match_oracle(cuda_mod):
     ox, oy = o.forecast(x0, uf, n_step, noise=True, w_eps=w_eps, x_eps=x_eps)
     assert_close(x.cpu().numpy(), ox, 2e-3, 2e-4, "forecast x")
     assert_close(yh.cpu().numpy(), oy, 2e-3, 2e-4, "forecast y")
+
+
+def test_sharded_two_gpus_match_single_gpu():
+    """Trials sharded over 2 GPUs (phase A | NCCL all-reduce | phase B) == the fused single-GPU run."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "scripts", "check_sharded.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
