@@ -67,7 +67,7 @@ def lorenz_poisson(T, B, D, seed, device=None):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
         self._stop_evt = threading.Event()
@@ -104,6 +104,16 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_traffic_per_time_step():
+    """DRAM bytes per time step of the persistent kernel from the committed ncu --set full capture (C2 shapes)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        t = json.load(open(p))
+        return float(t["dram_bytes_read_per_time_step"]) + float(t["dram_bytes_write_per_time_step"])
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -195,7 +205,7 @@ def run_ours(args, cfg):
 
     if world > 1:
         from vjf_b200.distributed import ShardedVJF
-        runner = ShardedVJF(model)
+        runner = ShardedVJF(model).connect()  # per-step all-reduce inside the persistent kernel (NVLink peer memory)
         step_dev = lambda: runner.run(y_dev)
         step_e2e = lambda: runner.run_host(y_host, mu_h, lv_h, ls_h)
     else:
@@ -269,13 +279,15 @@ def run_ours(args, cfg):
         peak, peak_src = measured_peak_gbs()
         algo_bytes = ALGO_BYTES_PER_TRIAL_STEP(cfg) * B * T  # per launch of the persistent kernel, per GPU
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        tps = measured_traffic_per_time_step() if (cfg["trials_per_gpu"] == C2["trials_per_gpu"] and world == 1) else None
         out = {"metric": "trial-steps/sec", "value": value, "unit": "trial-steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic (Lorenz-driven Poisson counts, random-init parameters)",
                "config": workload_config(cfg, world),
                "us_per_time_step": total_ms / args.steps / T * 1e3,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "vjf_persistent_kernel" if world == 1 else "vjf_phase_a_kernel+vjf_phase_b_kernel",
+                            "traffic": (tps * T if tps else None), "traffic_source": "profiles/traffic_r01.json (ncu dram__bytes_read+write per time step) x T",
+                            "algorithmic_bytes_per_launch": algo_bytes, "kernel": "vjf_persistent_kernel",
                             "algorithmic_bytes_per_trial_step": ALGO_BYTES_PER_TRIAL_STEP(cfg), "peak_source": peak_src,
                             "note": "B=4096 trials/step is latency-bound by the per-step serial chain (grid barriers + RLS factorisation), see DESIGN.md"},
                "e2e": {"value": units / e2e_s, "unit": "trial-steps/s", "h2d_bytes_per_step": int(y_host.numel() * 4),
@@ -302,7 +314,7 @@ def main():
     ap.add_argument("--T", type=int, default=None, help="time steps per bench step (default 256)")
     ap.add_argument("--chunk", type=int, default=32, help="time steps per H2D chunk in the e2e path")
     ap.add_argument("--spinup", type=float, default=1.0, help="seconds of extra untimed load so clocks leave idle")
-    ap.add_argument("--cpu-steps", type=int, default=200, help="time steps of the CPU baseline sample (~10-20 s)")
+    ap.add_argument("--cpu-steps", type=int, default=120, help="time steps of the CPU baseline sample (~10-20 s)")
     ap.add_argument("--ref-steps-per-step", type=int, default=16, help="--impl reference: time steps per bench step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -42,6 +42,7 @@ extern "C" {
 #define VJF_ST_ENTROPY_NONFINITE 4 /* entropy non-finite (model.py:144-145) */
 #define VJF_ST_MSE_NONFINITE 8     /* the reference would trip `assert isfinite(mse)` (functional.py:60) */
 #define VJF_ST_CHOL_FAILED 16      /* RLS Cholesky pivot <= 0: state left unchanged ('RLS failed.', module.py:112) */
+#define VJF_ST_COMM_TIMEOUT 32     /* a peer's contribution did not arrive within the timeout (sharded run) */
 
 /* dtype of the observation buffer handed to vjf_run / vjf_run_host */
 #define VJF_Y_F32 0
@@ -141,6 +142,22 @@ int vjf_step_phase_a(vjf_handle* h, int32_t B_local, int32_t B_global, const flo
                      const float* q_mean, const float* q_logvar, const float* eps, uint64_t seed, uint64_t step_index,
                      uint64_t trial_offset, uint32_t flags, float* out_mean, float* out_logvar, void* stream);
 int vjf_step_phase_b(vjf_handle* h, int32_t B_global, uint32_t flags, float lr, float* out_loss, void* stream);
+
+/* ---- trials sharded over GPUs, exchange INSIDE the persistent kernel over NVLink peer memory ----
+ * Every rank (one process per GPU) owns an exchange buffer; vjf_comm_local_handle() returns its 64-byte CUDA IPC
+ * handle, the caller gathers the handles of all ranks (torch.distributed, MPI, ...) and passes them to
+ * vjf_comm_connect().  vjf_run_sharded() is vjf_run() for the local block of trials: after the local slot
+ * reduction each CTA pushes its 512-byte chunk of sums to every peer's inbox with peer stores, waits for the
+ * matching chunks of the other ranks, adds them in rank order (=> bit-identical replicas) and goes on with the
+ * SGD / RLS phases -- compute and the all-reduce live in one kernel, no NCCL call on the step path.
+ * All ranks must call vjf_run_sharded with the same T / flags / lr in the same order. */
+#define VJF_MAX_RANKS 8
+int vjf_comm_local_handle(vjf_handle* h, void* out_handle64);
+int vjf_comm_connect(vjf_handle* h, int32_t rank, int32_t world, const void* handles /* [world][64] */);
+int vjf_run_sharded(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_global, uint64_t trial_offset, const void* y,
+                    int32_t y_dtype, const float* u, const float* q0_mean, const float* q0_logvar, const float* eps,
+                    uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu, float* logvar, float* losses,
+                    void* stream);
 
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);

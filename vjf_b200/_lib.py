@@ -8,7 +8,7 @@ MAX_LAYERS = 4
 MAX_XDIM = 16
 LIK = {"poisson": 0, "gaussian": 1}
 FLAG_SGD, FLAG_UPDATE, FLAG_WARMUP, FLAG_DECODER_FROZEN, FLAG_PRIOR_Q0 = 1, 2, 4, 8, 16
-ST_RECON_NONFINITE, ST_DYN_NONFINITE, ST_ENTROPY_NONFINITE, ST_MSE_NONFINITE, ST_CHOL_FAILED = 1, 2, 4, 8, 16
+ST_RECON_NONFINITE, ST_DYN_NONFINITE, ST_ENTROPY_NONFINITE, ST_MSE_NONFINITE, ST_CHOL_FAILED, ST_COMM_TIMEOUT = 1, 2, 4, 8, 16, 32
 Y_F32, Y_U8 = 0, 1
 
 
@@ -45,6 +45,9 @@ SIGNATURES = {
     "vjf_reduce_buffer": (_P, [_P]),
     "vjf_step_phase_a": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _P, _U64, _U64, _U64, _U32, _P, _P, _P]),
     "vjf_step_phase_b": (C.c_int, [_P, _I32, _U32, _F, _P, _P]),
+    "vjf_comm_local_handle": (C.c_int, [_P, _P]),
+    "vjf_comm_connect": (C.c_int, [_P, _I32, _I32, _P]),
+    "vjf_run_sharded": (C.c_int, [_P, _I32, _I32, _I32, _U64, _P, _I32, _P, _P, _P, _P, _U64, _U64, _U32, _F, _P, _P, _P, _P]),
     "vjf_get_status": (C.c_int, [_P, _P, C.POINTER(_U32), _I32]),
     "vjf_philox_normal": (C.c_int, [_U64, _U64, _U64, _I32, _I32, _P, _P]),
     "vjf_launch_count": (_I64, []),

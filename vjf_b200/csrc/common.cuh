@@ -62,6 +62,11 @@ struct StepParams {
   int T;
   int red_begin;   // first element of the partial vector the reduction touches
   long long* dbg;  // optional [T][8] per-phase globaltimer stamps of CTA 0 (development aid)
+  // ---- sharded run: exchange over peer memory ----
+  int world, rank;               // world == 1: single GPU
+  float* peer[VJF_MAX_RANKS];    // exchange buffer of every rank (peer-mapped); [world][2][PSx] floats then flags
+  int PSx;                       // PS rounded up to a multiple of 128
+  unsigned epoch0;               // epoch of time step 0 of this launch is epoch0 + 1
   int overlap;     // persistent schedule: CTA 0 is the dedicated RLS CTA, trial CTAs run the front half of step t+1 beside it
   int init_mode;   // phase B2 runs as RBFDS.initialize (vjf/model.py:379-388) instead of a filter step
 };
@@ -102,6 +107,21 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __threadfence();  // gpu-scope fence: also drops stale L1 lines before the CTA reads peers' data
   }
   __syncthreads();
+}
+
+// system-scope (cross-GPU) flag accessors for the in-kernel exchange
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
 }
 
 // Block-wide wait until a monotonically increasing device counter reaches `want` (producer side: fence + atomicAdd).
@@ -186,6 +206,8 @@ __device__ __forceinline__ float clip1(float g) { return g < -1.0f ? -1.0f : (g 
 
 // internal host API shared by the translation units
 struct vjf_handle {
+  // sharded run
+  float* xbuf; size_t xbuf_bytes; int comm_rank, comm_world; float* peer[VJF_MAX_RANKS]; unsigned comm_epoch;
   vjf_config cfg;
   vjf_layout lay64;
   StepParams base;       // dims, layout, pointers to workspace; per-call fields filled by the entry points

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
   }
   for (int t = 0; t < p.T; ++t) {
     unsigned masks = base_masks(p), fin;
+    const unsigned epoch = (p.world > 1) ? p.epoch0 + 1u + (unsigned)t : 0u;
     VJF_STAMP(p, t, 0);
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[t * 64 + 40] = clock64();
     for (int attempt = 0;; ++attempt) {
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       VJF_STAMP(p, t, 1);
       grid_barrier(p.barrier, target);
       VJF_STAMP(p, t, 2);
-      fin = term_finite_mask(p, p.partials, gridDim.x, sm);
+      fin = (p.world > 1) ? 7u : term_finite_mask(p, p.partials, gridDim.x, sm);  // sharded: decided on the global sums in B2
       // vjf/model.py:138-145: a non-finite term becomes the constant 0 => it must not contribute a
       // gradient either.  Rare; redo the trial-parallel phase with that term switched off.
       const unsigned nm = masks & (fin | ~7u);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       // factorisation as soon as the statistics chunks are reduced, while the trial CTAs finish the gradient
       // reduction + SGD, synchronise among themselves and go on to the front half of step t+1.
       if (trial_cta) {
-        phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x - 1, gridDim.x - 1, p.ctrl + 1);
+        phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x - 1, gridDim.x - 1, p.ctrl + 1, epoch);
         VJF_STAMP(p, t, 3);
         grid_barrier(p.ctrl + 2, target2, gridDim.x - 1);
         if (t + 1 < p.T) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         phase_b2(p, sm, t, fin);
       }
     } else {
-      phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x);
+      phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x, nullptr, epoch);
       VJF_STAMP(p, t, 3);
       grid_barrier(p.barrier, target);
       VJF_STAMP(p, t, 4);
@@ -332,6 +333,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   p.Gp = pad_mod32((int)up(hmax, 8), 8);
   p.ldw1 = pad_mod32((int)up(p.H[0], 4), 8);
   p.lik = cfg->likelihood;
+  p.world = 1;
   lay_to_int(lay, p.lay);
   p.G = p.lay.n_train;
   p.pa = p.G;
@@ -357,6 +359,8 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
 extern "C" int vjf_destroy(vjf_handle* h) {
   if (!h) return 0;
   cudaFree(h->partials); cudaFree(h->reduced); cudaFree(h->sync_words);
+  for (int r = 0; r < h->comm_world; ++r) if (r != h->comm_rank && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
+  cudaFree(h->xbuf);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->stage_y[i]); cudaFree(h->stage_u[i]); cudaFree(h->stage_eps[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -434,6 +438,56 @@ extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32
   p.mu = mu; p.logvar = logvar; p.losses = losses;
   p.seed = seed; p.step0 = step0; p.trial_offset = 0; p.flags = flags; p.lr = lr; p.T = T;
   p.dbg = g_dbg_ptr;
+  return launch_persistent(h, p, (cudaStream_t)stream);
+}
+
+// ---- sharded run: exchange buffers over CUDA IPC ----
+static size_t xbuf_floats(const StepParams& p) { return (size_t)VJF_MAX_RANKS * 2 * ((p.PS + 127) & ~127); }
+
+extern "C" int vjf_comm_local_handle(vjf_handle* h, void* out_handle64) {
+  if (!h || !out_handle64) { vjf_set_error("null argument"); return -1; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!h->xbuf) {
+    const size_t PSx = (h->base.PS + 127) & ~127;
+    h->xbuf_bytes = xbuf_floats(h->base) * sizeof(float) + (size_t)VJF_MAX_RANKS * (PSx / 128) * sizeof(unsigned) + 256;
+    VJF_CUDA_OK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
+    VJF_CUDA_OK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
+    VJF_CUDA_OK(cudaDeviceSynchronize());
+  }
+  VJF_CUDA_OK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out_handle64), h->xbuf));
+  return 0;
+}
+
+extern "C" int vjf_comm_connect(vjf_handle* h, int32_t rank, int32_t world, const void* handles) {
+  if (!h || !handles || world < 1 || world > VJF_MAX_RANKS || rank < 0 || rank >= world) { vjf_set_error("bad comm arguments (world <= %d)", VJF_MAX_RANKS); return -1; }
+  if (!h->xbuf) { vjf_set_error("call vjf_comm_local_handle first"); return -1; }
+  const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->peer[r] = h->xbuf; continue; }
+    void* ptr = nullptr;
+    VJF_CUDA_OK(cudaIpcOpenMemHandle(&ptr, hs[r], cudaIpcMemLazyEnablePeerAccess));
+    h->peer[r] = reinterpret_cast<float*>(ptr);
+  }
+  h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0;
+  return 0;
+}
+
+extern "C" int vjf_run_sharded(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_global, uint64_t trial_offset, const void* y,
+                               int32_t y_dtype, const float* u, const float* q0_mean, const float* q0_logvar, const float* eps,
+                               uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu, float* logvar, float* losses,
+                               void* stream) {
+  if (check_ptrs(h, y, u, q0_mean, q0_logvar, flags, mu, logvar)) return -1;
+  if (h->comm_world < 1) { vjf_set_error("vjf_comm_connect has not been called"); return -1; }
+  if (T < 1 || B_global < B_local) { vjf_set_error("bad T / batch sizes"); return -1; }
+  StepParams p = h->base;
+  if (plan_tiles(h, p, B_local, h->max_slots, 1)) return -1;
+  p.Bglobal = B_global;
+  p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
+  p.mu = mu; p.logvar = logvar; p.losses = losses;
+  p.seed = seed; p.step0 = step0; p.trial_offset = trial_offset; p.flags = flags; p.lr = lr; p.T = T;
+  p.world = h->comm_world; p.rank = h->comm_rank; p.PSx = (p.PS + 127) & ~127; p.epoch0 = h->comm_epoch;
+  for (int r = 0; r < p.world; ++r) p.peer[r] = h->peer[r];
+  h->comm_epoch += (unsigned)T;
   return launch_persistent(h, p, (cudaStream_t)stream);
 }
 

@@ -617,7 +617,7 @@ __device__ __forceinline__ bool sgd_applies(const StepParams& p, int e) {
 // end) are reduced first; when `signal` is given, every finished statistics chunk bumps it so that the RLS CTA
 // can start the factorisation without waiting for the gradient part.
 static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas,
-                                unsigned* signal = nullptr) {
+                                unsigned* signal = nullptr, unsigned epoch = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float invB = 1.0f / (float)p.Bglobal;
   float4* red = reinterpret_cast<float4*>(sm + p.s_b1);  // [16][32] float4
@@ -644,16 +644,46 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
     }
     red[warp * 32 + lane] = acc;
     __syncthreads();
-    if (warp == 0 && e0 < p.PS) {
+    if (warp == 0) {
       float4 t = red[lane];
 #pragma unroll
       for (int w = 1; w < VJF_NWARP; ++w) { const float4 v = red[w * 32 + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+      if (epoch) {
+        // ---- in-kernel all-reduce over NVLink peer memory: push this rank's chunk into every rank's inbox, raise the
+        //      (source rank, chunk) flag there, wait for the same chunk of every rank, add in rank order ----
+        const int par = epoch & 1, nchx = p.PSx >> 7;
+        const size_t flag_off = (size_t)p.world * 2 * p.PSx;
+        if (e0 < p.PS)
+          for (int r = 0; r < p.world; ++r)
+            *reinterpret_cast<float4*>(p.peer[r] + (size_t)(p.rank * 2 + par) * p.PSx + e0) = t;
+        __threadfence_system();
+        __syncwarp();
+        if (lane < p.world) {
+          st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[lane] + flag_off) + p.rank * nchx + ch, epoch);
+          const unsigned* wf = reinterpret_cast<const unsigned*>(p.peer[p.rank] + flag_off) + lane * nchx + ch;
+          const long long t0 = clock64();
+          while (ld_acquire_sys_u32(wf) < epoch) {
+            if (clock64() - t0 > 6000000000ll) { atomicOr(p.status, (unsigned)VJF_ST_COMM_TIMEOUT); break; }  // ~3 s
+          }
+        }
+        __syncwarp();
+        __threadfence_system();
+        if (e0 < p.PS) {
+          t = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = 0; r < p.world; ++r) {
+            const float4 v = ld_volatile_f4(p.peer[p.rank] + (size_t)(r * 2 + par) * p.PSx + e0);
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+          }
+        }
+      }
+      if (e0 < p.PS) {
       *reinterpret_cast<float4*>(p.reduced + e0) = t;
       if (apply && e0 < p.lay.n_train) {
         const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (sgd_applies(p, e0 + i)) p.state[e0 + i] -= p.lr * clip1(tv[i] * invB);
+      }
       }
     }
     __syncthreads();
@@ -1018,6 +1048,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   const bool warm = p.flags & VJF_FLAG_WARMUP;
   const bool upd = p.flags & VJF_FLAG_UPDATE;
 
+  if (p.world > 1) finmask = (isfinite(scal[SC_RECON]) ? 1u : 0u) | (isfinite(scal[SC_DYN]) ? 2u : 0u) | (isfinite(scal[SC_ENT]) ? 4u : 0u);
   if (tid == 0 && !p.init_mode) {
     unsigned stbits = 0;
     float l_recon = scal[SC_RECON] / Bf, l_dyn = scal[SC_DYN] / Bf, h = scal[SC_ENT] / Bf;

@@ -57,6 +57,25 @@ class ShardedVJF:
         n = int(lib.vjf_reduce_size(model._h))
         ptr = lib.vjf_reduce_buffer(model._h)
         self.reduce_buf = torch.as_tensor(_DevBuf(ptr, n), device=model.device)
+        self.fused = False
+
+    def connect(self):
+        """Exchange the CUDA IPC handles of the per-rank exchange buffers so that the persistent kernel can do the
+        per-step all-reduce itself over NVLink peer memory (vjf_run_sharded)."""
+        if self.world == 1:
+            return self
+        m, lib = self.m, self.m._lib
+        hbuf = C.create_string_buffer(64)
+        with torch.cuda.device(m.device):
+            _lib.check(lib.vjf_comm_local_handle(m._h, hbuf))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+        with torch.cuda.device(m.device):
+            _lib.check(lib.vjf_comm_connect(m._h, self.rank, self.world, blob))
+        dist.barrier(group=self.group)
+        self.fused = True
+        return self
 
     @torch.no_grad()
     def run(self, y, u=None, *, sgd=True, update=True, warm_up=False, eps=None, trial_offset=None):
@@ -77,6 +96,13 @@ class ShardedVJF:
         frozen = not m.decoder.decode.weight.requires_grad
         p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
         s = m._stream()
+        if self.fused and self.world > 1:
+            f = plan_step(0, sgd, update, warm_up, frozen)
+            with torch.cuda.device(m.device):
+                _lib.check(lib.vjf_run_sharded(m._h, T, B, Bg, off, p(y), ydt, p(u), None, None, p(eps), m.seed, m._step_index, f,
+                                               m.lr, p(mu), p(lv), p(losses), s))
+            m._step_index += T
+            return mu, lv, losses
         for t in range(T):
             f = plan_step(t, sgd, update, warm_up, frozen)
             _lib.check(lib.vjf_step_phase_a(m._h, B, Bg, p(y[t]), ydt, p(None if u is None else u[t]),
