@@ -203,17 +203,33 @@ def run_ours(args, cfg):
     y_host = y_dev.cpu().pin_memory()
     mu_h = torch.empty(T, B, d).pin_memory(); lv_h = torch.empty(T, B, d).pin_memory(); ls_h = torch.empty(T, 4).pin_memory()
 
+    # Every bench step is "the first epoch of a fit": it starts from the same initial parameters (a 70 KB
+    # device-to-device copy inside the timed region).  The information-form RLS accumulates phi^T phi / v without
+    # forgetting (shrink = 1, vjf/model.py:371); in fp32 -- the reference's dtype too -- it degrades after a few
+    # 1e6 samples (~1500 time steps at 4096 trials), so an unbounded number of back-to-back epochs would time a
+    # different, degenerate regime.
+    state0 = model._flat.clone()
     if world > 1:
         from vjf_b200.distributed import ShardedVJF
         runner = ShardedVJF(model).connect()  # per-step all-reduce inside the persistent kernel (NVLink peer memory)
-        step_dev = lambda: runner.run(y_dev)
-        step_e2e = lambda: runner.run_host(y_host, mu_h, lv_h, ls_h)
+
+        def step_dev():
+            model._flat.copy_(state0)
+            return runner.run(y_dev)
+
+        def step_e2e():
+            model._flat.copy_(state0)
+            runner.run_host(y_host, mu_h, lv_h, ls_h)
     else:
-        step_dev = lambda: model.run(y_dev)
+        def step_dev():
+            model._flat.copy_(state0)
+            return model.run(y_dev)
         flags = _lib.FLAG_SGD | _lib.FLAG_UPDATE | _lib.FLAG_PRIOR_Q0
         p = lambda t: C.c_void_p(t.data_ptr())
 
         def step_e2e():
+            model._flat.copy_(state0)
+            torch.cuda.current_stream().synchronize()
             _lib.check(lib.vjf_run_host(model._h, T, B, p(y_host), _lib.Y_F32, None, None, model.seed, model._step_index, flags,
                                         model.lr, p(mu_h), p(lv_h), p(ls_h), args.chunk))
             model._step_index += T
@@ -224,19 +240,13 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
 
     # ---- warm-up (also brings the clocks up from idle) ----
-    # The information-form RLS accumulates phi^T phi / v without forgetting (shrink = 1, vjf/model.py:371);
-    # in fp32 -- the reference's dtype too -- it degrades after a few 1e6 samples.  Every timed region
-    # therefore starts from the initial parameters, like the first epochs of a fit().
-    state0 = model._flat.clone()
     for _ in range(max(3, args.warmup)):
         step_dev()
     torch.cuda.synchronize()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < args.spinup:
-        model._flat.copy_(state0)
         step_dev()
         torch.cuda.synchronize()
-    model._flat.copy_(state0)
     model.status()
 
     # ---- timed region: device-resident inputs ----
@@ -258,9 +268,7 @@ def run_ours(args, cfg):
     status = model.status()
 
     # ---- timed region: end to end through the C ABI with pinned host buffers ----
-    model._flat.copy_(state0)
     step_e2e()
-    model._flat.copy_(state0)
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):

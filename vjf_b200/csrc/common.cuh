@@ -39,6 +39,7 @@ struct StepParams {
   int s_in, s_g, s_phi, s_act[VJF_MAX_LAYERS], s_gpa, s_gpb, s_eps, s_xu, s_xt, s_mt, s_lt, s_pm, s_dx, s_gxt, s_gmt,
       s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_scf, s_b1, s_inl, s_phil, s_gpal, s_gpbl, s_total;
   int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
+  int in_split;  // the staged input matrix is kept as a presplit (hi, lo) pair (needs a second rows x K1p array)
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
   float* state;

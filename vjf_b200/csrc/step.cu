@@ -209,12 +209,13 @@ static int pad_mod32(int lo, int tgt) {
 
 // shared-memory plan for a tile of `tb` trials (rows padded to a multiple of 16 for the MMA tiles);
 // returns the number of floats (maximum over phase A, B1 and B2)
-static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem, bool w1_in_smem) {
+static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem, bool w1_in_smem, bool in_split) {
   const int rows = (tb + 15) & ~15;
   size_t off = 0;
   auto take = [&](size_t n) { size_t at = off; off = (off + n + 3) & ~(size_t)3; return (int)at; };
   p.s_in = take((size_t)rows * p.K1p);
-  p.s_inl = take((size_t)rows * p.K1p);
+  p.in_split = in_split ? 1 : 0;
+  p.s_inl = in_split ? take((size_t)rows * p.K1p) : p.s_in;
   p.s_g = take((size_t)((tb + 3) & ~3) * p.Dp);  // only real trials are read back
   p.s_phi = take((size_t)rows * p.Rp);
   p.s_phil = take((size_t)rows * p.Rp);
@@ -265,9 +266,11 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots, int pe
   bool u_smem = (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
   bool dec_smem = (size_t)(p.d + 1) * p.D * 4 <= 32 * 1024;
   bool w1_smem = (size_t)p.K1 * p.ldw1 * 4 <= 72 * 1024;
+  bool in_split = true;
   int tb = want;
   for (;;) {
-    if (plan_smem(p, tb, u_smem, dec_smem, w1_smem) * 4 <= limit) break;
+    if (plan_smem(p, tb, u_smem, dec_smem, w1_smem, in_split) * 4 <= limit) break;
+    if (in_split && (size_t)16 * p.K1p * 4 > 48 * 1024) { in_split = false; continue; }  // wide observations: split on the fly
     if (w1_smem && tb <= want - 8) { w1_smem = false; tb = want; continue; }
     if (tb > 4) { tb -= 4; continue; }
     if (w1_smem) { w1_smem = false; tb = want; continue; }

@@ -118,7 +118,7 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
       float eta = db[j];
 #pragma unroll
       for (int k = 0; k < DX; ++k) { w[k] = (DX == d || k < d) ? dw[k * D + j] : 0.f; eta = fmaf(w[k], xt[k], eta); }
-      const float yv = yb[j] + ybl[j];  // the staged observations are a (hi, lo) pair
+      const float yv = p.in_split ? yb[j] + ybl[j] : yb[j];  // the staged observations may be a (hi, lo) pair
       float g;
       if (p.lik == VJF_LIK_GAUSSIAN) {
         // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
@@ -300,7 +300,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
         phil_s[b * Rp + k] = v - h;
       }
     }
-    presplit_inplace(in_s, inl_s, rows * K1p);
+    if (p.in_split) presplit_inplace(in_s, inl_s, rows * K1p);
     __syncthreads();
 
     VJF_STAMP(p, t, 11);
@@ -310,7 +310,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       for (int l = 0; l < L; ++l) {
         float* out = sm + p.s_act[l];
         const bool w_sm = (l == 0) && p.W1_in_smem;
-        mma_linear_fwd(A, (l == 0) ? inl_s : nullptr, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
+        mma_linear_fwd(A, (l == 0 && p.in_split) ? inl_s : nullptr, lda, K, w_sm ? (sm + p.s_W1) : (st + p.lay.mlp_w[l]), w_sm ? p.ldw1 : p.H[l], st + p.lay.mlp_b[l], p.H[l], out,
                        p.Hp[l], rows, true);
         // zero the remaining pad columns (beyond roundup(H,8)) read by the weight-gradient fragments
         const int h8 = (p.H[l] + 7) & ~7, h16 = (p.H[l] + 15) & ~15;
@@ -504,7 +504,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
       const int ldp = (l == 0) ? K1p : p.Hp[l - 1];
       const int Kl = (l == 0) ? K1 : p.H[l - 1];
-      mma_wgrad(Aprev, (l == 0) ? inl_s : nullptr, ldp, Kl, gcur, gcurl, Gp, p.H[l], rows, slot + p.lay.mlp_w[l], first);
+      mma_wgrad(Aprev, (l == 0 && p.in_split) ? inl_s : nullptr, ldp, Kl, gcur, gcurl, Gp, p.H[l], rows, slot + p.lay.mlp_w[l], first);
       tile_colsum(gcur, gcurl, Gp, p.H[l], nb, slot + p.lay.mlp_b[l], first);
       if (l > 0) {
         const float* Wl = st + p.lay.mlp_w[l];  // [Kl][H_l]
