@@ -17,6 +17,8 @@ torch.cuda.synchronize()
 dbg = torch.zeros(T, 64, dtype=torch.int64, device="cuda")
 lib.vjf_debug_set_stamps.argtypes = [C.c_void_p]; lib.vjf_debug_set_stamps.restype = None
 lib.vjf_debug_set_stamps(C.c_void_p(dbg.data_ptr()))
+lib.vjf_debug_set_cta.argtypes = [C.c_int]; lib.vjf_debug_set_cta.restype = None
+lib.vjf_debug_set_cta(int(os.environ.get('PCTA', 1)))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); m.run(y); e1.record(); torch.cuda.synchronize()
 lib.vjf_debug_set_stamps(None)
@@ -38,6 +40,13 @@ for i, j, n in back:
     print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
 b2 = [(4, 24, "losses/lik"), (24, 25, "load P,A,W,b + g"), (25, 26, "rows init+publish"), (26, 27, "LDL sweep"), (27, 28, "scale+commit"),
       (28, 29, "W'=Uz"), (29, 5, "residual/var")]
+# timeline of one step relative to CTA 0's step start (mean over steps)
+tl = [("cta0 arrive bar1", 1, 0), ("cta0 bar1 released", 2, 0), ("cta0 B2 start", 4, 0), ("cta0 B2 end", 5, 0), ("cta0 bar3 released", 6, 0),
+      ("trial back start (after cp.async wait)", 10, 0), ("trial back end", 20, 0), ("trial B1 end", 23, 0), ("trial barrier released", 21, 0), ("trial front prologue issued", 7, 0), ("trial front(t+1) tile loads issued", 22, 1), ("trial front(t+1) staged", 8, 1), ("trial front(t+1) end", 19, 1)]
+print(f" timeline (us after step start; trial CTA {os.environ.get('PCTA', 1)}):")
+for n, i, dt in tl:
+    a = s[5 + dt:-2 + dt if -2 + dt else None, i] - s[5:-2, 0]
+    print(f"  {n:40s} {a.mean().item()/1e3:7.2f}")
 print(" phase B2 stages (CTA 0):")
 for i, j, n in b2:
     print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")

@@ -40,6 +40,11 @@ struct StepParams {
       s_glt, s_plv, s_U, s_W, s_c, s_iw, s_red, s_dec, s_qp, s_W1, s_hm, s_hv, s_flag, s_scf, s_b1, s_inl, s_phil, s_gpal, s_gpbl, s_total;
   int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
   int in_split;  // the staged input matrix is kept as a presplit (hi, lo) pair (needs a second rows x K1p array)
+  int dbg_cta;   // development aid: which trial CTA drops the phase-A stamps
+  float* w1_mirror;  // [K1][ldw1] row-padded copy of the recognition layer-1 weight (workspace), the TMA source
+  int use_tma;   // TMA bulk staging of the layer-1 weight / decoder and prefetch of the next observation tile (overlapped schedule)
+  int use_umma;  // layer-1 weight gradient on tcgen05 (umma.cuh): overlapped schedule, one hidden layer of <= 64 units
+  int umma_nk;   // roundup(K1, 8): the N extent of that MMA
   int ldm;  // row stride of the factorisation workspace in phase B2
   // ---- pointers ----
   float* state;
@@ -90,6 +95,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -198,7 +206,7 @@ __device__ __forceinline__ long long gtime_ns() {
 // stamp into slot idx of step t (64 slots per step)
 #define VJF_STAMP(p, t, idx)                                                              \
   do {                                                                                    \
-    if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (idx) >= 7 && (idx) <= 23) ? 1 : 0)) \
+    if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (idx) >= 7 && (idx) <= 23) ? (p).dbg_cta : 0)) \
       (p).dbg[(t) * 64 + (idx)] = gtime_ns();                                             \
   } while (0)
 

@@ -43,13 +43,38 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
   const bool trial_cta = blockIdx.x > 0;
   const bool early_rls = p.overlap && p.lik == VJF_LIK_POISSON;
   const unsigned n_stat_chunks = (unsigned)(((p.PS + 127) >> 7) - (p.pa >> 7));
+  // Blackwell asynchronous machinery of the overlapped schedule (step_kernels.cuh, TileCtx): every trial CTA owns
+  // 256 TMEM columns (tcgen05 weight gradient) and three mbarriers (tcgen05 commit, TMA weights, TMA observations)
+  TileCtx ctx{0u, 0u, 0u, 0u, -1, 0, 0};
+  TileCtx* cx = nullptr;
+  if (p.overlap && trial_cta && (p.use_umma || p.use_tma)) {
+    cx = &ctx;
+    ctx.flags = (p.use_umma ? CX_UMMA : 0) | (p.use_tma ? CX_TMA : 0);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + p.s_flag + 1);
+    if (p.use_umma && threadIdx.x < 32) tmem_alloc256(tslot);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 3; ++i) mbar_init(reinterpret_cast<uint64_t*>(sm + p.s_flag + 2 + 2 * i), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (p.use_umma) ctx.tmem = *tslot;
+  }
+  if (p.use_tma) {  // (re)build the row-padded mirror of the layer-1 weight; first read after the first grid barrier
+    const int n = p.K1 * p.H[0];
+    for (int i = blockIdx.x * VJF_NT + threadIdx.x; i < n; i += gridDim.x * VJF_NT) {
+      const int r = i / p.H[0];
+      p.w1_mirror[r * p.ldw1 + (i - r * p.H[0])] = p.state[p.lay.mlp_w[0] + i];
+    }
+  }
   if (p.overlap) {
     if (!trial_cta) {
       float* slot = p.partials;  // CTA 0 owns no trials: its slot stays zero
       for (int i = threadIdx.x; i < p.PS; i += VJF_NT) slot[i] = 0.f;
     } else {
-      phase_a_prologue(p, sm, STAGE_FRONT);
-      phase_a_tile(p, sm, 0, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+      phase_a_prologue(p, sm, STAGE_FRONT, cx);
+      phase_a_tile(p, sm, 0, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
     }
   }
   for (int t = 0; t < p.T; ++t) {
@@ -62,12 +87,12 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         phase_a(p, sm, t, masks);
       } else if (trial_cta) {
         phase_a_prologue(p, sm, STAGE_BACK);
-        phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK);
+        phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK, cx);
       }
       VJF_STAMP(p, t, 1);
       grid_barrier(p.barrier, target);
       VJF_STAMP(p, t, 2);
-      fin = (p.world > 1) ? 7u : term_finite_mask(p, p.partials, gridDim.x, sm);  // sharded: decided on the global sums in B2
+      fin = (p.world > 1 || ld_acquire_u32(p.ctrl + 3) != (unsigned)(t + 1)) ? 7u : term_finite_mask(p, p.partials, gridDim.x, sm);  // sharded: decided on the global sums in B2
       // vjf/model.py:138-145: a non-finite term becomes the constant 0 => it must not contribute a
       // gradient either.  Rare; redo the trial-parallel phase with that term switched off.
       const unsigned nm = masks & (fin | ~7u);
@@ -75,8 +100,8 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         masks = nm;
         grid_barrier(p.barrier, target);
         if (p.overlap && trial_cta) {
-          phase_a_prologue(p, sm, STAGE_FRONT);
-          phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_FRONT);
+          phase_a_prologue(p, sm, STAGE_FRONT, cx);
+          phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_FRONT, cx);
         }
         continue;
       }
@@ -89,10 +114,13 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       if (trial_cta) {
         phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x - 1, gridDim.x - 1, p.ctrl + 1, epoch);
         VJF_STAMP(p, t, 3);
+        VJF_STAMP(p, t, 23);
         grid_barrier(p.ctrl + 2, target2, gridDim.x - 1);
+        VJF_STAMP(p, t, 21);
         if (t + 1 < p.T) {
-          phase_a_prologue(p, sm, STAGE_FRONT);
-          phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+          phase_a_prologue(p, sm, STAGE_FRONT, cx);
+          VJF_STAMP(p, t, 7);
+          phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
         }
       } else {
         VJF_STAMP(p, t, 3);
@@ -108,13 +136,18 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       if (blockIdx.x == 0) {
         phase_b2(p, sm, t, fin);
       } else if (p.overlap && t + 1 < p.T) {
-        phase_a_prologue(p, sm, STAGE_FRONT);
-        phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT);
+        phase_a_prologue(p, sm, STAGE_FRONT, cx);
+        phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
       }
     }
     VJF_STAMP(p, t, 5);
     grid_barrier(p.barrier, target);
     VJF_STAMP(p, t, 6);
+  }
+  if (cx && p.use_umma) {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_free256(ctx.tmem);
   }
 }
 
@@ -239,7 +272,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_W1 = take(w1_in_smem ? (size_t)p.K1 * p.ldw1 : 0);
   p.s_hm = take((size_t)p.H[p.L - 1] * p.d);
   p.s_hv = take((size_t)p.H[p.L - 1] * p.d + p.d);
-  p.s_flag = take(4);
+  p.s_flag = take(8);  // [0] flag, [1] TMEM base, [2..7] three mbarriers
   p.s_scf = take(VJF_NSCAL);
   p.s_b1 = take(2048 + 8);
   p.s_W = take((size_t)p.R * p.d);
@@ -283,6 +316,17 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots, int pe
   p.TB = tb;
   p.ntiles = (B + tb - 1) / tb;
   if (p.overlap && p.ntiles > max_slots) p.overlap = 0;  // the tile had to shrink to fit shared memory
+  // layer-1 weight gradient on tcgen05 (umma.cuh): one tile per CTA (the operand pair aliases the staged W1, which
+  // must not be needed by a later tile), one hidden layer of at most 64 units (M = 64), N = roundup(K1, 8) <= 256
+  {
+    const int rows = (tb + 15) & ~15, nk = (p.K1 + 7) & ~7;
+    static const bool no_umma = getenv("VJF_B200_NO_UMMA") != nullptr;
+    p.umma_nk = nk;
+    static const bool no_tma = getenv("VJF_B200_NO_TMA") != nullptr;
+    p.use_tma = (!no_tma && p.overlap && (p.D & 3) == 0 && (p.H[0] & 3) == 0 && ((p.H[p.L - 1] * p.d) & 3) == 0) ? 1 : 0;
+    p.use_umma = (!no_umma && p.overlap && p.L == 1 && p.H[0] <= 64 && p.Gp >= 64 && p.W1_in_smem && nk <= 256 &&
+                  (size_t)p.K1 * p.ldw1 >= (size_t)2 * nk * rows) ? 1 : 0;
+  }
   p.nslots = p.overlap ? p.ntiles + 1 : std::min(p.ntiles, max_slots + (persistent && max_slots < h->max_slots ? 1 : 0));
   return 0;
 }
@@ -349,8 +393,11 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   const size_t part_bytes = (size_t)h->max_slots * p.PS * sizeof(float);
   VJF_CUDA_OK(cudaMalloc(&h->partials, part_bytes));
   VJF_CUDA_OK(cudaMemset(h->partials, 0, part_bytes));
-  VJF_CUDA_OK(cudaMalloc(&h->reduced, (size_t)p.PS * sizeof(float)));
-  VJF_CUDA_OK(cudaMemset(h->reduced, 0, (size_t)p.PS * sizeof(float)));
+  // reduced vector, followed by the row-padded mirror of the recognition layer-1 weight (TMA source, 128-byte aligned)
+  const size_t red_floats = (size_t)up(p.PS, 32) + (size_t)p.K1 * p.ldw1;
+  VJF_CUDA_OK(cudaMalloc(&h->reduced, red_floats * sizeof(float)));
+  VJF_CUDA_OK(cudaMemset(h->reduced, 0, red_floats * sizeof(float)));
+  p.w1_mirror = h->reduced + up(p.PS, 32);
   VJF_CUDA_OK(cudaMalloc(&h->sync_words, 64 * sizeof(unsigned)));
   VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
   p.partials = h->partials; p.reduced = h->reduced;
@@ -425,7 +472,9 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
 
 // development aid (not part of the public header): per-phase timestamps of CTA 0 for the next launches
 static long long* g_dbg_ptr = nullptr;
+static int g_dbg_cta = 1;
 extern "C" void vjf_debug_set_stamps(long long* dev_ptr) { g_dbg_ptr = dev_ptr; }
+extern "C" void vjf_debug_set_cta(int cta) { g_dbg_cta = cta; }
 extern "C" int vjf_debug_read_sweep(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, g_sweep_ticks, sizeof(long long) * 160); }
 
 extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32_t y_dtype, const float* u,
@@ -441,6 +490,7 @@ extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32
   p.mu = mu; p.logvar = logvar; p.losses = losses;
   p.seed = seed; p.step0 = step0; p.trial_offset = 0; p.flags = flags; p.lr = lr; p.T = T;
   p.dbg = g_dbg_ptr;
+  p.dbg_cta = g_dbg_cta;
   return launch_persistent(h, p, (cudaStream_t)stream);
 }
 

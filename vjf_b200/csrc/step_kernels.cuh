@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "mma.cuh"
+#include "umma.cuh"
 
 // ------------------------------------------------------------------------------------------
 // tile GEMM helpers (SIMT fp32; rows is a multiple of 4, leading dimensions are multiples of 4)
@@ -180,7 +181,29 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
 #define PART_BOTH 0
 #define PART_FRONT 1
 #define PART_BACK 2
-static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part) {
+// Per-CTA context of the overlapped persistent schedule (one tile per trial CTA): the Blackwell asynchronous machinery.
+//   CX_UMMA: layer-1 weight gradient on tcgen05 / TMEM (umma.cuh)
+//   CX_TMA : recognition layer-1 weight + decoder staged by TMA bulk copies (waited just before they are needed, not at
+//            the start of the tile), and the observation tile of step t+1 prefetched (cp.async) at the end of the back
+//            half of step t, so that its HBM latency hides behind the reduction / barriers
+// mbarriers live in shared memory at s_flag + 2 (umma) and + 4 (weights); *_phase = parity to wait for.
+#define CX_UMMA 1
+#define CX_TMA 2
+struct TileCtx { uint32_t tmem, umma_phase, w_phase, y_phase; int y_ready_t, flags, consts_staged; };
+typedef TileCtx UmmaCtx;
+
+// bytes the front prologue moves by TMA
+static __device__ __forceinline__ uint32_t tma_head_bytes(const StepParams& p) { return 16u * (((uint32_t)p.H[p.L - 1] * p.d + 3u) >> 2); }
+static __device__ __forceinline__ uint32_t tma_front_bytes(const StepParams& p) {
+  return (p.W1_in_smem ? (uint32_t)p.K1 * p.ldw1 * 4u : 0u) + (p.dec_in_smem ? (uint32_t)(p.d + 1) * p.D * 4u : 0u) + 2u * tma_head_bytes(p) +
+         16u * (((uint32_t)p.d + 3u) >> 2);
+}
+
+static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part,
+                                                    TileCtx* cx = nullptr) {
+  TileCtx* uc = (cx && (cx->flags & CX_UMMA)) ? cx : nullptr;
+  const bool tma = cx && (cx->flags & CX_TMA);
+  const bool cx_overlap = p.overlap && part != PART_BOTH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, L = p.L;
   const int K1 = p.K1, K1p = p.K1p, Rp = p.Rp, Gp = p.Gp;
@@ -211,8 +234,6 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   for (int i = 0; i < VJF_NSCAL; ++i) sc[i] = 0.f;
 
   if (part != PART_BACK) {
-    const float lam = st[p.lay.lik_logvar];
-    const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
     // ---- S0: stage the tile: in = [y | u | m_s | l_s | 0] (vjf/recognition.py:32-37), eps, zero pads ----
     {
       const size_t row0 = (size_t)t * p.B + b0;
@@ -220,7 +241,44 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
       const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
       const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-      for (int b = warp; b < rows; b += VJF_NWARP) {
+      // observation tile prefetched (cp.async) during the previous back half?  (a prefetch for another step -- the redo
+      // path re-runs the front half of the same step -- is drained and dropped)
+      bool y_there = false;
+      if (tma && cx->y_ready_t >= 0) {
+        y_there = (cx->y_ready_t == t);
+        cx->y_ready_t = -1;
+        if (!y_there) { cp_async_wait_all(); __syncthreads(); }
+      }
+      if (y_there) {
+        // fast path of the overlapped schedule: the observations are already in place (prefetch), the previous
+        // posterior of this tile is still in shared memory (mt_s / lt_s of the previous front half), and the rest is
+        // spread over all threads instead of one warp per trial
+        for (int i = tid; i < nb * Ep; i += VJF_NT) {
+          const int b = i / Ep, e = i - b * Ep;
+          float v = 0.f;
+          if (e < u) v = p.u_in[(row0 + b) * u + e];
+          else if (e < u + d) v = mt_s[b * d + e - u];
+          else if (e < E) v = lt_s[b * d + e - u - d];
+          in_s[b * K1p + D + e] = v;
+        }
+        if (p.eps) {
+          for (int i = tid; i < nb * 2 * d; i += VJF_NT) {
+            const int b = i / (2 * d), k = i - b * 2 * d;
+            const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
+            eps_s[i] = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d];
+          }
+        } else {
+          const int nblk = (d + 3) >> 2;
+          for (int i = tid; i < nb * 2 * nblk; i += VJF_NT) {
+            const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
+            float z[4];
+            philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
+            for (int k = 0; k < 4; ++k)
+              if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
+          }
+        }
+      }
+      for (int b = (y_there ? nb : 0) + warp; b < rows; b += VJF_NWARP) {
         float* dst = in_s + b * K1p;
         if (b < nb) {
           if ((D & 3) == 0) {
@@ -271,9 +329,10 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     __syncthreads();
 
     VJF_STAMP(p, t, 8);
-    if (first) {  // finish the staged RBF widths: -1/(2 w^2)
+    if (first && !(tma && cx->consts_staged)) {  // finish the staged RBF widths: -1/(2 w^2)
       for (int i = tid; i < R; i += VJF_NT) { const float w = expf(iw_s[i]); iw_s[i] = -0.5f / (w * w); }
     }
+    if (tma) cx->consts_staged = 1;
     // ---- S1: xs = m_s + eps1 * exp(l_s / 2) (vjf/util.py:11-13); xu = [xs, u] (util.py:38-49) ----
     for (int i = tid; i < nb * du; i += VJF_NT) {
       const int b = i / du, k = i - b * du;
@@ -305,6 +364,10 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
 
     VJF_STAMP(p, t, 11);
     // ---- S4: recognition MLP (vjf/recognition.py:31-42) on the tensor cores ----
+    if (tma) {  // layer-1 weight, decoder and head weights: TMA bulk copies issued by the prologue
+      mbar_wait(reinterpret_cast<uint64_t*>(sm + p.s_flag + 4), cx->w_phase);
+      cx->w_phase ^= 1u;
+    }
     {
       const float* A = in_s; int lda = K1p, K = K1;
       for (int l = 0; l < L; ++l) {
@@ -318,6 +381,26 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
           for (int i = tid; i < rows * (h16 - h8); i += VJF_NT) out[(i / (h16 - h8)) * p.Hp[l] + h8 + i % (h16 - h8)] = 0.f;
         __syncthreads();
         A = out; lda = p.Hp[l]; K = p.H[l];
+      }
+    }
+    if (uc) {
+      // tcgen05 path of the layer-1 weight gradient (back half): its B operand is the input matrix with the trials as the
+      // K dimension, in the canonical K-major layout [(b/4)][k1][b%4] as a (hi, lo) pair.  The staged W1 is dead after S4,
+      // so the pair is built in its place here, off the critical path.
+      const int NK = p.umma_nk, nq = rows >> 2;
+      float* bh = sm + p.s_W1;
+      float* bl = bh + NK * rows;
+      for (int i = tid; i < nq * NK; i += VJF_NT) {
+        const int q = i / NK, k = i - q * NK;
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = in_s[(4 * q + j) * K1p + k];
+          if (p.in_split) { h[j] = x; l[j] = inl_s[(4 * q + j) * K1p + k]; }
+          else { h[j] = tf32_hi(x); l[j] = x - h[j]; }
+        }
+        *reinterpret_cast<float4*>(bh + 4 * i) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(bl + 4 * i) = make_float4(l[0], l[1], l[2], l[3]);
       }
     }
     VJF_STAMP(p, t, 12);
@@ -350,6 +433,14 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     VJF_STAMP(p, t, 13);
     // ---- S5/S6: decoder eta = D xt + bias (model.py:29-30), likelihood terms, dloss/deta (times B), g_xt = g_eta D,
     //      decoder gradients.  Specialised on the state dimension so that xt and the accumulators live in registers.
+    // Gaussian likelihood: its logvar is updated by the RLS CTA (GaussianLikelihood.update) concurrently with this front
+    // half in the overlapped schedule -- wait until the value of the previous step is final, then read it past L1
+    float lam = 0.f;
+    if (p.lik == VJF_LIK_GAUSSIAN) {
+      if (cx_overlap && t > 0) wait_counter(p.ctrl + 4, (unsigned)t);
+      lam = __ldcg(st + p.lay.lik_logvar);
+    }
+    const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
     switch (d) {
       case 1: decoder_stage<1>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
       case 2: decoder_stage<2>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
@@ -483,6 +574,24 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     }
     // g_pre of the last hidden layer: (g_mt W_m + g_lt W_v) * (1 - h^2); pad columns up to a multiple of 8 are zero
     const int H8 = (HL + 7) & ~7;
+    if (uc) {
+      // tcgen05 path: G^T [64 x rows] in the canonical K-major layout (K = trials), pads zero
+      for (int b = warp; b < rows; b += VJF_NWARP) {
+        for (int n = lane; n < 64; n += 32) {
+          float v = 0.f;
+          if (n < HL && b < nb) {
+            float s = 0.f;
+            for (int k = 0; k < d; ++k) { s = fmaf(gmt_s[b * d + k], hm_s[n * d + k], s); s = fmaf(glt_s[b * d + k], hv_s[n * d + k], s); }
+            const float h = hL[b * ldh + n];
+            v = s * (1.0f - h * h);
+          }
+          const float vh = tf32_hi(v);
+          const int o = umma_canon(n, b, 64);
+          gpa[o] = vh;
+          gpal[o] = v - vh;
+        }
+      }
+    } else
     for (int b = warp; b < nb; b += VJF_NWARP) {
       for (int n = lane; n < H8; n += 32) {
         float v = 0.f;
@@ -500,6 +609,18 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     __syncthreads();
     VJF_STAMP(p, t, 17);
     float* gcur = gpa; float* gnext = gpb; float* gcurl = gpal; float* gnextl = gpbl;
+    if (uc) {
+      // bias gradient = column sums of g_pre, then the weight gradient on tcgen05 / TMEM
+      if (tid < HL) {
+        float s = 0.f;
+        for (int b = 0; b < nb; ++b) { const int o = umma_canon(tid, b, 64); s += gpa[o] + gpal[o]; }
+        acc_store(slot + p.lay.mlp_b[0] + tid, s, first);
+      }
+      const float* bh = sm + p.s_W1;
+      umma_wgrad(gpa, gpal, bh, bh + p.umma_nk * rows, p.umma_nk, K1, HL, rows, uc->tmem, 0u,
+                 reinterpret_cast<uint64_t*>(sm + p.s_flag + 2), uc->umma_phase, slot + p.lay.mlp_w[0], first);
+      uc->umma_phase ^= 1u;
+    } else
     for (int l = L - 1; l >= 0; --l) {
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
       const int ldp = (l == 0) ? K1p : p.Hp[l - 1];
@@ -542,8 +663,18 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
     if (tid == 6) acc_store(slot + p.lay.lik_logvar, s, first);  // Gaussian d loss / d lambda (times B)
     else acc_store(slot + p.ps + tid, s, first);
+    // a loss-term partial that is not comfortably finite: tell the grid to take the exact (slow) check of the sums
+    if (tid < 3 && !(fabsf(s) < 1e30f)) atomicMax(p.ctrl + 3, (unsigned)(t + 1));
   }
   __syncthreads();
+  if (tma && part == PART_BACK && t + 1 < p.T && p.y_dtype != VJF_Y_U8 && (D & 3) == 0) {
+    // prefetch the observations of step t+1 into the (now dead) input matrix; the copies land while the grid reduces
+    const float* src = reinterpret_cast<const float*>(p.y) + ((size_t)(t + 1) * p.B + b0) * D;
+    const int c4 = D >> 2;
+    for (int i = tid; i < nb * c4; i += VJF_NT) { const int b = i / c4, c = (i - b * c4) << 2; cp_async16(in_s + b * K1p + c, src + (size_t)b * D + c); }
+    cp_async_commit();
+    cx->y_ready_t = t + 1;
+  }
   VJF_STAMP(p, t, 20);
 }
 
@@ -552,21 +683,53 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
 // step of the previous time step is done.  STAGE_BACK: w_mean / w_chol -- final once its RLS is done.
 #define STAGE_FRONT 1
 #define STAGE_BACK 2
-static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what) {
+static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what, TileCtx* cx = nullptr) {
   const int tid = threadIdx.x;
+  const bool tma = cx && (cx->flags & CX_TMA);
   const float* st = p.state;
   const int HL = p.H[p.L - 1];
   if (what & STAGE_FRONT) {
-    stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
-    stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
-    stage_async(sm + p.s_hm, p.d, st + p.lay.head_m_w, p.d, HL, p.d, tid, VJF_NT);
-    stage_async(sm + p.s_hv, p.d, st + p.lay.head_v_w, p.d, HL, p.d, tid, VJF_NT);
-    stage_async(sm + p.s_hv + HL * p.d, p.d, st + p.lay.head_v_b, p.d, 1, p.d, tid, VJF_NT);
-    if (p.dec_in_smem) {
-      stage_async(sm + p.s_dec, p.D, st + p.lay.dec_w, p.D, p.d, p.D, tid, VJF_NT);
-      stage_async(sm + p.s_dec + p.d * p.D, p.D, st + p.lay.dec_b, p.D, 1, p.D, tid, VJF_NT);
+    // RBF centres and widths are not trained (vjf/module.py:115-130: requires_grad=False) and the RLS does not touch
+    // them: with a dedicated tile per CTA they are staged once per launch
+    if (!tma || !cx->consts_staged) {
+      stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
+      stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
     }
-    if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
+    if (!tma) {
+      stage_async(sm + p.s_hm, p.d, st + p.lay.head_m_w, p.d, HL, p.d, tid, VJF_NT);
+      stage_async(sm + p.s_hv, p.d, st + p.lay.head_v_w, p.d, HL, p.d, tid, VJF_NT);
+      stage_async(sm + p.s_hv + HL * p.d, p.d, st + p.lay.head_v_b, p.d, 1, p.d, tid, VJF_NT);
+    }
+    if (tma) {
+      // the two big ones by TMA bulk copies issued by one thread, completion on an mbarrier that the tile waits on right
+      // before S4 -- S0..S2 run while the data is in flight.  The layer-1 weight comes from its row-padded mirror
+      // (StepParams::w1_mirror, kept up to date by the SGD step), so that ONE copy lands it in the bank-conflict-free
+      // layout the MMA fragments want.  The sources were written by other CTAs through the generic proxy (ordered by
+      // the grid barrier): fence.proxy.async orders the async-proxy reads after them.
+      const uint32_t bytes = tma_front_bytes(p);
+      if (tid == 0) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(sm + p.s_flag + 4);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(bar, bytes);
+        if (p.W1_in_smem) tma_bulk_g2s(sm + p.s_W1, p.w1_mirror, (uint32_t)p.K1 * p.ldw1 * 4u, bar);
+        if (p.dec_in_smem) {
+          tma_bulk_g2s(sm + p.s_dec, st + p.lay.dec_w, (uint32_t)p.d * p.D * 4u, bar);
+          tma_bulk_g2s(sm + p.s_dec + p.d * p.D, st + p.lay.dec_b, (uint32_t)p.D * 4u, bar);
+        }
+        // head weights [H_L][d] and the logvar-head bias (sizes rounded up to 16 bytes: the state segments and the
+        // shared arrays are padded)
+        const uint32_t hb = tma_head_bytes(p);
+        tma_bulk_g2s(sm + p.s_hm, st + p.lay.head_m_w, hb, bar);
+        tma_bulk_g2s(sm + p.s_hv, st + p.lay.head_v_w, hb, bar);
+        tma_bulk_g2s(sm + p.s_hv + HL * p.d, st + p.lay.head_v_b, 16u * ((p.d + 3) >> 2), bar);
+      }
+    } else {
+      if (p.dec_in_smem) {
+        stage_async(sm + p.s_dec, p.D, st + p.lay.dec_w, p.D, p.d, p.D, tid, VJF_NT);
+        stage_async(sm + p.s_dec + p.d * p.D, p.D, st + p.lay.dec_b, p.D, 1, p.D, tid, VJF_NT);
+      }
+      if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
+    }
   }
   if (what & STAGE_BACK) {
     stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
@@ -628,16 +791,16 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e0 < p.PS) {
       const float* q = src + e0;
-      int c = warp;
-      for (; c + 3 * VJF_NWARP < nslots; c += 4 * VJF_NWARP) {
-        const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
-        const float4 v1 = *reinterpret_cast<const float4*>(q + (size_t)(c + VJF_NWARP) * p.PS);
-        const float4 v2 = *reinterpret_cast<const float4*>(q + (size_t)(c + 2 * VJF_NWARP) * p.PS);
-        const float4 v3 = *reinterpret_cast<const float4*>(q + (size_t)(c + 3 * VJF_NWARP) * p.PS);
-        acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
-        acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+      // up to 10 slots per warp (nslots <= 160): issue every load before the first add, one L2 round trip in all
+      float4 v[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const int c = warp + j * VJF_NWARP;
+        v[j] = (c < nslots) ? *reinterpret_cast<const float4*>(q + (size_t)c * p.PS) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (; c < nslots; c += VJF_NWARP) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+      for (int c = warp + 10 * VJF_NWARP; c < nslots; c += VJF_NWARP) {
         const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
         acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
       }
@@ -680,9 +843,17 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
       *reinterpret_cast<float4*>(p.reduced + e0) = t;
       if (apply && e0 < p.lay.n_train) {
         const float tv[4] = {t.x, t.y, t.z, t.w};
+        // the row-padded mirror of the layer-1 weight (TMA source) is kept current; e0 and H are multiples of 4, so the
+        // four elements of a lane share a row
+        const int w0 = e0 - p.lay.mlp_w[0];
+        float* mir = (p.use_tma && w0 >= 0 && w0 < p.K1 * p.H[0]) ? p.w1_mirror + (w0 / p.H[0]) * p.ldw1 + (w0 % p.H[0]) : nullptr;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (sgd_applies(p, e0 + i)) p.state[e0 + i] -= p.lr * clip1(tv[i] * invB);
+          if (sgd_applies(p, e0 + i)) {
+            const float v = p.state[e0 + i] - p.lr * clip1(tv[i] * invB);
+            p.state[e0 + i] = v;
+            if (mir) mir[i] = v;
+          }
       }
       }
     }
@@ -1071,6 +1242,9 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
       st[p.lay.lik_logvar] = logf(var);
       st[p.lay.lik_n] = n_new;
     }
+    // overlapped schedule: the front half of step t+1 runs concurrently and needs this logvar for its decoder stage --
+    // publish "logvar of step t is final" (the trial CTAs wait for it there)
+    if (p.overlap && p.lik == VJF_LIK_GAUSSIAN) { __threadfence(); st_release_gpu_u32(p.ctrl + 4, (unsigned)(t + 1)); }
   }
   VJF_STAMP(p, t, 24);
   if (!upd) return;

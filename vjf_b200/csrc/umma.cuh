@@ -41,6 +41,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n"
       ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// ---- TMA bulk copies (global -> shared, completion counted in bytes on an mbarrier) ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst, src and bytes must be multiples of 16
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -83,14 +92,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 //     dW[k1][n] (+)= sum_b in[b][k1] * G[b][n]      computed as D[M = 64 (n)][N = NK (k1)] = G^T [64 x rows] * in_b [NK x rows]^T
 // Operands (3xTF32: hi and lo arrays each) in the canonical K-major layout with K = trials:
 //     gt_*  : [64 x rows]  (MN = 64),  element (n, b)      in_b_* : [NK x rows] (MN = NK), element (k1, b),   NK = roundup(K1, 8) <= 224
+// (`bar` is an mbarrier initialised once per kernel with count 1; `phase` = parity of its current phase.)
 // One thread issues rows/8 k-steps x 3 MMAs (lo*hi, hi*lo, hi*hi) accumulating in TMEM columns [tcol, tcol + NK); 8 warps
 // then read the accumulator back (row n lives in TMEM lane n % 16 + 32 * (n / 16)) and store/add it to the slot.
 __device__ __forceinline__ void umma_wgrad(const float* gt_hi, const float* gt_lo, const float* inb_hi, const float* inb_lo, int NK, int K1, int H,
-                                           int rows, uint32_t tmem_base, uint32_t tcol, uint64_t* bar, float* dW, bool first) {
+                                           int rows, uint32_t tmem_base, uint32_t tcol, uint64_t* bar, uint32_t phase, float* dW, bool first) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // operands were written with ordinary shared-memory stores: make them visible to the async proxy, then hand over
   fence_async_smem();
-  if (tid == 0) mbar_init(bar, 1);
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
@@ -108,30 +117,21 @@ __device__ __forceinline__ void umma_wgrad(const float* gt_hi, const float* gt_l
     }
     umma_commit(bar);
   }
-  mbar_wait(bar, 0);
+  mbar_wait(bar, phase);
   tc_fence_after();
-  // epilogue: warps 0..7 ; sub-partition q = warp % 4 holds rows n = 16q .. 16q+15 in its lanes 0..15 ; the two warp
-  // groups split the 32-column chunks
-  if (warp < 8) {
+  // epilogue: a warp reaches the TMEM lanes of sub-partition q = warp % 4, which hold rows n = 16q .. 16q+15 in lanes
+  // 0..15 (M = 64 layout) ; the four warp groups split the 32-column chunks
+  {
     const int q = warp & 3, grp = warp >> 2, n = 16 * q + lane;
-    for (int c0 = grp * 32; c0 < NK; c0 += 64) {
+    for (int c0 = grp * 32; c0 < NK; c0 += 32 * (VJF_NT / 128)) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tcol + c0;
-      if (c0 + 32 <= NK) {
-        float v[32];
-        tmem_ld32(taddr, v);
-        if (lane < 16 && n < H) {
+      // the allocation is 256 columns wide, so a full 32-column read is always legal; columns >= K1 are not stored
+      float v[32];
+      tmem_ld32(taddr, v);
+      if (lane < 16 && n < H) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < K1) { float* o = dW + (size_t)(c0 + j) * H + n; if (first) *o = v[j]; else atomicAdd(o, v[j]); }
-        }
-      } else {
-        float v[16];
-        tmem_ld16(taddr, v);
-        if (lane < 16 && n < H) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < K1) { float* o = dW + (size_t)(c0 + j) * H + n; if (first) *o = v[j]; else atomicAdd(o, v[j]); }
-        }
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < K1) { float* o = dW + (size_t)(c0 + j) * H + n; if (first) *o = v[j]; else atomicAdd(o, v[j]); }
       }
     }
   }
