@@ -276,6 +276,30 @@ def run_ours(args, cfg):
     barrier()
     e2e_s = time.perf_counter() - w0
 
+    # ---- the same end-to-end call with the spike counts handed over as uint8 (numpy counts are a valid `fit` input of the
+    #      reference too, vjf/model.py:243-245 coerces them); 4x fewer PCIe bytes.  Reported beside the fp32 number. ----
+    e2e_u8 = None
+    if world == 1:
+        y_u8 = y_host.to(torch.uint8)
+        if bool((y_u8.to(torch.float32) == y_host).all()):
+            y_u8 = y_u8.pin_memory()
+
+            def step_e2e_u8():
+                model._flat.copy_(state0)
+                torch.cuda.current_stream().synchronize()
+                _lib.check(lib.vjf_run_host(model._h, T, B, p(y_u8), _lib.Y_U8, None, None, model.seed, model._step_index, flags,
+                                            model.lr, p(mu_h), p(lv_h), p(ls_h), args.chunk))
+                model._step_index += T
+            step_e2e_u8()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e_u8()
+            torch.cuda.synchronize()
+            e2e_u8 = {"value": B * T * args.steps / (time.perf_counter() - w0), "unit": "trial-steps/s", "h2d_bytes_per_step": int(y_u8.numel()),
+                      "d2h_bytes_per_step": int((mu_h.numel() + lv_h.numel() + ls_h.numel()) * 4),
+                      "api": "vjf_run_host with y_dtype = VJF_Y_U8 (counts as bytes)", "status_word": int(model.status())}
+
     if world > 1:
         tt = torch.tensor([total_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -303,6 +327,8 @@ def run_ours(args, cfg):
                        "api": "vjf_run_host (C ABI, pinned host buffers, chunked H2D overlapped with compute)"},
                "gpu_launches": int(launches), "clocks": clocks, "status_word": int(status),
                "status_word_e2e": int(model.status())}
+        if e2e_u8:
+            out["e2e_u8"] = e2e_u8
         if world == 1 and not args.no_cpu:
             val, dt = cpu_port_rate(cfg, B, args.cpu_steps)
             out["cpu_baseline"] = {"value": val, "unit": "trial-steps/s", "cores": os.cpu_count(), "kind": "port",

@@ -14,7 +14,7 @@ from vjf_b200.model import VJF
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-D, d, R, H, Bg, T = 60, 3, 20, [16], 200, 12
+D, d, R, H, Bg, T = 60, 3, 20, [int(os.environ.get("CS_H", 16))], 200, 12
 for lik in ("poisson", "gaussian"):
     torch.manual_seed(7)  # identical data on every rank
     y = (torch.poisson(torch.full((T, Bg, D), 0.8)) if lik == "poisson" else torch.randn(T, Bg, D)).cuda()

@@ -47,6 +47,12 @@ print(f" timeline (us after step start; trial CTA {os.environ.get('PCTA', 1)}):"
 for n, i, dt in tl:
     a = s[5 + dt:-2 + dt if -2 + dt else None, i] - s[5:-2, 0]
     print(f"  {n:40s} {a.mean().item()/1e3:7.2f}")
+fine = [(13, 41, "decoder rows (warp 0)"), (41, 42, "decoder sync"), (42, 18, "decoder grads -> slot"),
+        (17, 43, "colsum + umma wgrad"), (43, 44, "scalar warp sums + sync"), (44, 45, "scalar store + sync"), (45, 20, "y prefetch issue")]
+print(" fine stamps (trial CTA):")
+for i, j, n in fine:
+    print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
+print(f"  prologue: proxy fences {(s[0,48]-s[0,47]).item()/1e3:.2f} us (last step)")
 print(" phase B2 stages (CTA 0):")
 for i, j, n in b2:
     print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")

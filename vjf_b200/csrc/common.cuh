@@ -168,10 +168,12 @@ __device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned
   float u1 = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
   float u2 = ((float)(c[2] >> 8) + 1.0f) * (1.0f / 16777216.0f);
   float u3 = (float)(c[3] >> 8) * (1.0f / 16777216.0f);
-  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  // hardware transcendentals (MUFU): the draw sits on the critical path of every step and noise needs no last-bit accuracy;
+  // the tape generator (vjf_philox_normal) runs this same code, so in-kernel and tape mode still agree bit for bit
+  float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
   float s0, c0, s1, c1;
-  sincosf(TWO_PI * u1, &s0, &c0);
-  sincosf(TWO_PI * u3, &s1, &c1);
+  __sincosf(TWO_PI * (u1 - 0.5f), &s0, &c0);
+  __sincosf(TWO_PI * (u3 - 0.5f), &s1, &c1);
   out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
 }
 
@@ -206,7 +208,7 @@ __device__ __forceinline__ long long gtime_ns() {
 // stamp into slot idx of step t (64 slots per step)
 #define VJF_STAMP(p, t, idx)                                                              \
   do {                                                                                    \
-    if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (idx) >= 7 && (idx) <= 23) ? (p).dbg_cta : 0)) \
+    if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (((idx) >= 7 && (idx) <= 23) || ((idx) >= 41 && (idx) <= 55))) ? (p).dbg_cta : 0)) \
       (p).dbg[(t) * 64 + (idx)] = gtime_ns();                                             \
   } while (0)
 

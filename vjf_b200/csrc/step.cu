@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       const int r = i / p.H[0];
       p.w1_mirror[r * p.ldw1 + (i - r * p.H[0])] = p.state[p.lay.mlp_w[0] + i];
     }
+    grid_barrier(p.barrier, target);  // the front half of step 0 reads the mirror (TMA) right away
   }
   if (p.overlap) {
     if (!trial_cta) {

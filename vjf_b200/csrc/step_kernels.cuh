@@ -103,7 +103,7 @@ __device__ __forceinline__ float load_y(const StepParams& p, size_t idx) {
 template <int DX>
 static __device__ __forceinline__ void decoder_stage(const StepParams& p, float* sm, int nb, bool first, bool r_on, float lam,
                                                      float p_lam, float e_nlam, const float* dw, const float* db, float* slot,
-                                                     float* sc) {
+                                                     float* sc, int t = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, K1p = p.K1p, Dp = p.Dp;
   const float* in_s = sm + p.s_in; float* g_s = sm + p.s_g; const float* xt_s = sm + p.s_xt; float* gxt_s = sm + p.s_gxt;
@@ -151,7 +151,9 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
       if (lane == 0 && k < d) gxt_s[b * d + k] = s;
     }
   }
+  VJF_STAMP(p, t, 41);
   __syncthreads();
+  VJF_STAMP(p, t, 42);
   float* gdw = slot + p.lay.dec_w;
   float* gdb = slot + p.lay.dec_b;
   for (int j = tid; j < D; j += VJF_NT) {
@@ -444,7 +446,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     switch (d) {
       case 1: decoder_stage<1>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
       case 2: decoder_stage<2>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
-      case 3: decoder_stage<3>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
+      case 3: decoder_stage<3>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc, t); break;
       case 4: decoder_stage<4>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc); break;
       default: if (d <= 8) decoder_stage<8>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
                else decoder_stage<16>(p, sm, nb, first, r_on, lam, p_lam, e_nlam, dw, db, slot, sc);
@@ -620,6 +622,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       umma_wgrad(gpa, gpal, bh, bh + p.umma_nk * rows, p.umma_nk, K1, HL, rows, uc->tmem, 0u,
                  reinterpret_cast<uint64_t*>(sm + p.s_flag + 2), uc->umma_phase, slot + p.lay.mlp_w[0], first);
       uc->umma_phase ^= 1u;
+      VJF_STAMP(p, t, 43);
     } else
     for (int l = L - 1; l >= 0; --l) {
       const float* Aprev = (l == 0) ? in_s : (sm + p.s_act[l - 1]);
@@ -658,6 +661,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     if (lane == 0) red_s[warp * VJF_NSCAL + i] = s;
   }
   __syncthreads();
+  VJF_STAMP(p, t, 44);
   if (tid < VJF_NSCAL) {
     float s = (part == PART_BACK) ? scf_s[tid] : 0.f;
     for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
@@ -667,6 +671,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     if (tid < 3 && !(fabsf(s) < 1e30f)) atomicMax(p.ctrl + 3, (unsigned)(t + 1));
   }
   __syncthreads();
+  VJF_STAMP(p, t, 45);
   if (tma && part == PART_BACK && t + 1 < p.T && p.y_dtype != VJF_Y_U8 && (D & 3) == 0) {
     // prefetch the observations of step t+1 into the (now dead) input matrix; the copies land while the grid reduces
     const float* src = reinterpret_cast<const float*>(p.y) + ((size_t)(t + 1) * p.B + b0) * D;
@@ -709,7 +714,10 @@ static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what
       const uint32_t bytes = tma_front_bytes(p);
       if (tid == 0) {
         uint64_t* bar = reinterpret_cast<uint64_t*>(sm + p.s_flag + 4);
-        asm volatile("fence.proxy.async;" ::: "memory");
+        VJF_STAMP(p, 0, 47);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        VJF_STAMP(p, 0, 48);
         mbar_expect_tx(bar, bytes);
         if (p.W1_in_smem) tma_bulk_g2s(sm + p.s_W1, p.w1_mirror, (uint32_t)p.K1 * p.ldw1 * 4u, bar);
         if (p.dec_in_smem) {
