@@ -40,6 +40,7 @@ __device__ __forceinline__ unsigned base_masks(const StepParams& p) {
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float sm[];
   unsigned target = 0, target2 = 0;
+  bool back_staged = false;  // w_chol / w_mean of the coming back half already staged (issued behind the RLS tail)
   const bool trial_cta = blockIdx.x > 0;
   const bool early_rls = p.overlap && p.lik == VJF_LIK_POISSON;
   const unsigned n_stat_chunks = (unsigned)(((p.PS + 127) >> 7) - (p.pa >> 7));
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       if (!p.overlap) {
         phase_a(p, sm, t, masks);
       } else if (trial_cta) {
-        phase_a_prologue(p, sm, STAGE_BACK);
+        if (!back_staged) phase_a_prologue(p, sm, STAGE_BACK);
+        back_staged = false;
         phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK, cx);
       }
       VJF_STAMP(p, t, 1);
@@ -122,6 +124,10 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
           phase_a_prologue(p, sm, STAGE_FRONT, cx);
           VJF_STAMP(p, t, 7);
           phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
+          // w_chol / w_mean of step t are published before the RLS CTA finishes the step: stage them now, behind its tail
+          wait_counter(p.ctrl + 5, (unsigned)(t + 1));
+          phase_a_prologue(p, sm, STAGE_BACK);
+          back_staged = true;
         }
       } else {
         VJF_STAMP(p, t, 3);
@@ -139,6 +145,9 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       } else if (p.overlap && t + 1 < p.T) {
         phase_a_prologue(p, sm, STAGE_FRONT, cx);
         phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
+        wait_counter(p.ctrl + 5, (unsigned)(t + 1));
+        phase_a_prologue(p, sm, STAGE_BACK);
+        back_staged = true;
       }
     }
     VJF_STAMP(p, t, 5);

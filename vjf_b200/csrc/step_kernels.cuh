@@ -1114,6 +1114,9 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     Wout[i] = w; Ws[i] = w;
   }
   __syncthreads();
+  // overlapped schedule: w_chol / w_mean of this step are final -- let the trial CTAs stage them for the back half of the
+  // next step while the residual / state-noise update below is still running
+  if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
   VJF_STAMP(p, t, 29);
   // ---- sum |dx - phi W'|^2 - S = <W', A W'> - 2 <W', b> from the statistics still in registers / shared memory ----
   double acc = 0.0;
@@ -1255,7 +1258,10 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     if (p.overlap && p.lik == VJF_LIK_GAUSSIAN) { __threadfence(); st_release_gpu_u32(p.ctrl + 4, (unsigned)(t + 1)); }
   }
   VJF_STAMP(p, t, 24);
-  if (!upd) return;
+  if (!upd) {
+    if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
+    return;
+  }
   const float gam = st[p.lay.tr_logvar];
   // rls(x, target, v): v = exp(state logvar) in a filter step (model.py:371); in initialize v is the
   // mean squared increment (model.py:384-385)
@@ -1278,6 +1284,8 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
   }
+  // every path (failed factorisation, shared-memory fallback, warm-up) ends with final RLS outputs here
+  if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
 
   // ---- state-noise running variance (vjf/model.py:373-377).  sum |dx - phi W'|^2 from the reduced
   //      statistics: S - 2 <W', b> + <W', A W'>, evaluated in double ----
