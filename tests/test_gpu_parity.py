@@ -99,7 +99,11 @@ def test_persistent_run_equals_stepwise(cuda_mod, name):
 
 
 @pytest.mark.parametrize("lik,B,D,d,u,R,H", [("poisson", 300, 200, 3, 0, 50, [64]), ("gaussian", 130, 50, 4, 2, 32, [32, 16]),
-                                             ("gaussian", 1, 20, 2, 0, 100, [20]), ("poisson", 777, 64, 8, 0, 64, [128])])
+                                             ("gaussian", 1, 20, 2, 0, 100, [20]), ("poisson", 777, 64, 8, 0, 64, [128]),
+                                             # BASELINE C4 shape (ydim 2000, xdim 8; input matrix too wide for the presplit pair),
+                                             # C5 shape (xdim 4, 1024 trials), and more tiles than CTAs (plain schedule)
+                                             ("poisson", 48, 2000, 8, 0, 64, [128]), ("gaussian", 1024, 50, 4, 0, 32, [32]),
+                                             ("poisson", 5000, 40, 3, 0, 20, [16])])
 def test_seeded_steps_match_oracle(cuda_mod, lik, B, D, d, u, R, H):
     """Seeded synthetic inputs at shapes the oracle finishes in seconds: 6 steps, every output and the
     whole state compared with the fp64 oracle."""
@@ -121,6 +125,33 @@ def test_seeded_steps_match_oracle(cuda_mod, lik, B, D, d, u, R, H):
     tol = dict(rtol=2e-2, atol=2e-3) if B == 1 else dict(rtol=1e-3, atol=1e-4)
     compare_state(cuda_mod.state_np(m), o.get_state(), **tol)
     assert m.status() == 0
+
+
+def test_fit_epochs_equal_runs_and_learn(cuda_mod):
+    """VJF.fit (vjf/model.py:223-307) drives the persistent kernel epoch by epoch: same numbers as calling run()
+    per epoch by hand with the same flags, finite, and the loss goes down on a learnable synthetic sequence."""
+    from vjf_b200.model import VJF
+    rng = np.random.default_rng(3)
+    T, B, D, d = 80, 3, 12, 2
+    th = np.linspace(0, 8 * np.pi, T)[:, None] + rng.uniform(0, 2 * np.pi, (1, B))
+    x = np.stack([np.cos(th), np.sin(th)], -1)                      # (T, B, 2) limit cycle
+    Cm = rng.normal(size=(2, D)) * 0.8
+    y = (x @ Cm + 0.1 * rng.normal(size=(T, B, D))).astype(np.float32)
+    a = VJF.make_model(D, d, 0, 10, [16], "gaussian", lr=1e-3, max_trials=B, seed=5)
+    b = VJF.make_model(D, d, 0, 10, [16], "gaussian", lr=1e-3, max_trials=B, seed=5)
+    b.load_full_state(a.full_state())
+    mu, lv, loss = a.fit(y, max_iter=4, progress=False, rtol=0.0)   # rtol 0: stays in warm-up, 4 epochs
+    first = last = None
+    for i in range(4):
+        bmu, blv, bl = b.run(torch.as_tensor(y), None, None, sgd=True, update=True, warm_up=True)
+        b.scheduler.step()   # per-epoch lr decay (model.py:303)
+        last = bl[:, 0].mean().item()
+        first = last if first is None else first
+    assert torch.equal(mu, bmu) and torch.equal(lv, blv)
+    assert torch.equal(a._flat, b._flat)
+    assert np.isfinite(last) and abs(float(loss) - last) <= 1e-6 * abs(last)
+    assert last < first, (first, last)
+    assert a.status() == 0
 
 
 def test_philox_tape_equals_in_kernel_draws(cuda_mod):
