@@ -827,7 +827,8 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
         if (e0 < p.PS)
           for (int r = 0; r < p.world; ++r)
             *reinterpret_cast<float4*>(p.peer[r] + (size_t)(p.rank * 2 + par) * p.PSx + e0) = t;
-        __threadfence_system();
+        // the warp barrier orders every lane's stores before the flag lanes' st.release.sys (cumulativity): no separate
+        // system-scope fence is needed, and it would cost a second NVLink round trip
         __syncwarp();
         if (lane < p.world) {
           st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[lane] + flag_off) + p.rank * nchx + ch, epoch);
@@ -837,8 +838,7 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
             if (clock64() - t0 > 6000000000ll) { atomicOr(p.status, (unsigned)VJF_ST_COMM_TIMEOUT); break; }  // ~3 s
           }
         }
-        __syncwarp();
-        __threadfence_system();
+        __syncwarp();  // the polling lanes' ld.acquire.sys + this barrier order the inbox reads below after the peers' data
         if (e0 < p.PS) {
           t = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int r = 0; r < p.world; ++r) {
