@@ -38,8 +38,8 @@ for i, j, n in front:
 print(" back half:")
 for i, j, n in back:
     print(f"  {n:30s} {(s[5:-1, j] - s[5:-1, i]).mean().item()/1e3:7.2f} us")
-b2 = [(4, 24, "losses/lik"), (24, 25, "load P,A,W,b + g"), (25, 26, "rows init+publish"), (26, 27, "LDL sweep"), (27, 28, "scale+commit"),
-      (28, 29, "W'=Uz"), (29, 5, "residual/var")]
+b2 = [(4, 30, "P, W, PW preload + stats wait"), (30, 25, "A, b -> P', g"), (25, 26, "rows init+publish"), (26, 27, "LDL sweep"), (27, 28, "scale+commit"),
+      (28, 29, "W'=Uz"), (29, 5, "residual/var + losses")]
 # timeline of one step relative to CTA 0's step start (mean over steps)
 tl = [("cta0 arrive bar1", 1, 0), ("cta0 bar1 released", 2, 0), ("cta0 B2 start", 4, 0), ("cta0 B2 end", 5, 0), ("cta0 bar3 released", 6, 0),
       ("trial back start (after cp.async wait)", 10, 0), ("trial back end", 20, 0), ("trial B1 end", 23, 0), ("trial barrier released", 21, 0), ("trial front prologue issued", 7, 0), ("trial front(t+1) tile loads issued", 22, 1), ("trial front(t+1) staged", 8, 1), ("trial front(t+1) end", 19, 1)]

@@ -109,6 +109,7 @@ def test_seeded_steps_match_oracle(cuda_mod, lik, B, D, d, u, R, H):
     whole state compared with the fp64 oracle."""
     from vjf_b200.model import VJF
     rng = np.random.default_rng(5)
+    torch.manual_seed(5)  # make_model draws the initial parameters from torch's generator
     T = 6
     m = VJF.make_model(D, d, u, R, H, lik, lr=1e-3, max_trials=B)
     o = O.OracleVJF(D, d, u, R, H, lik, lr=1e-3, dtype=np.float64)
@@ -122,7 +123,8 @@ def test_seeded_steps_match_oracle(cuda_mod, lik, B, D, d, u, R, H):
     assert_close(lv.cpu().numpy(), olv, 2e-4, 2e-5, "logvar")
     assert_close(losses.cpu().numpy(), olosses, 2e-4, 2e-3, "losses")
     # B=1 with 100 RBFs is the ill-conditioned fp32 RLS recipe (see test_run_matches_reference): looser there
-    tol = dict(rtol=2e-2, atol=2e-3) if B == 1 else dict(rtol=1e-3, atol=1e-4)
+    # 30 000 samples into the fp32 information-form RLS (B = 5000): its rounding error grows with the sample count
+    tol = dict(rtol=2e-2, atol=2e-3) if B == 1 else (dict(rtol=2e-3, atol=2e-4) if B >= 4096 else dict(rtol=1e-3, atol=1e-4))
     compare_state(cuda_mod.state_np(m), o.get_state(), **tol)
     assert m.status() == 0
 

@@ -41,6 +41,7 @@ struct StepParams {
   int U_in_smem, dec_in_smem, W1_in_smem, ldw1;
   int in_split;  // the staged input matrix is kept as a presplit (hi, lo) pair (needs a second rows x K1p array)
   int dbg_cta;   // development aid: which trial CTA drops the phase-A stamps
+  float* u_mirror;   // [roundup(R,8)][ldu] row-padded copy of w_chol (workspace), the TMA source of the back half
   float* w1_mirror;  // [K1][ldw1] row-padded copy of the recognition layer-1 weight (workspace), the TMA source
   int use_tma;   // TMA bulk staging of the layer-1 weight / decoder and prefetch of the next observation tile (overlapped schedule)
   int use_umma;  // layer-1 weight gradient on tcgen05 (umma.cuh): overlapped schedule, one hidden layer of <= 64 units
@@ -111,8 +112,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
   if (threadIdx.x == 0) {
     __threadfence();
     red_release_add_u32(counter, 1u);
-    while (ld_acquire_u32(counter) < target) {
-    }
+    while (ld_acquire_u32(counter) < target) __nanosleep(32);  // back off: ~130 pollers share one L2 line with the arriving atomics
     __threadfence();  // gpu-scope fence: also drops stale L1 lines before the CTA reads peers' data
   }
   __syncthreads();
@@ -136,8 +136,7 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
 // Block-wide wait until a monotonically increasing device counter reaches `want` (producer side: fence + atomicAdd).
 __device__ __forceinline__ void wait_counter(const unsigned* counter, unsigned want) {
   if (threadIdx.x == 0) {
-    while (ld_acquire_u32(counter) < want) {
-    }
+    while (ld_acquire_u32(counter) < want) __nanosleep(32);
     __threadfence();
   }
   __syncthreads();

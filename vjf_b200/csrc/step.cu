@@ -68,6 +68,10 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       const int r = i / p.H[0];
       p.w1_mirror[r * p.ldw1 + (i - r * p.H[0])] = p.state[p.lay.mlp_w[0] + i];
     }
+    for (int i = blockIdx.x * VJF_NT + threadIdx.x; i < p.R * p.R; i += gridDim.x * VJF_NT) {
+      const int r = i / p.R;
+      p.u_mirror[r * p.ldu + (i - r * p.R)] = p.state[p.lay.w_chol + i];
+    }
     grid_barrier(p.barrier, target);  // the front half of step 0 reads the mirror (TMA) right away
   }
   if (p.overlap) {
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       if (!p.overlap) {
         phase_a(p, sm, t, masks);
       } else if (trial_cta) {
-        if (!back_staged) phase_a_prologue(p, sm, STAGE_BACK);
+        if (!back_staged) phase_a_prologue(p, sm, STAGE_BACK, cx);
         back_staged = false;
         phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK, cx);
       }
@@ -126,14 +130,13 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
           phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
           // w_chol / w_mean of step t are published before the RLS CTA finishes the step: stage them now, behind its tail
           wait_counter(p.ctrl + 5, (unsigned)(t + 1));
-          phase_a_prologue(p, sm, STAGE_BACK);
+          phase_a_prologue(p, sm, STAGE_BACK, cx);
           back_staged = true;
         }
       } else {
         VJF_STAMP(p, t, 3);
-        wait_counter(p.ctrl + 1, n_stat_chunks * (unsigned)(t + 1));
         VJF_STAMP(p, t, 4);
-        phase_b2(p, sm, t, fin);
+        phase_b2(p, sm, t, fin, p.ctrl + 1, n_stat_chunks * (unsigned)(t + 1));
       }
     } else {
       phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x, nullptr, epoch);
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         phase_a_prologue(p, sm, STAGE_FRONT, cx);
         phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
         wait_counter(p.ctrl + 5, (unsigned)(t + 1));
-        phase_a_prologue(p, sm, STAGE_BACK);
+        phase_a_prologue(p, sm, STAGE_BACK, cx);
         back_staged = true;
       }
     }
@@ -404,10 +407,11 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaMalloc(&h->partials, part_bytes));
   VJF_CUDA_OK(cudaMemset(h->partials, 0, part_bytes));
   // reduced vector, followed by the row-padded mirror of the recognition layer-1 weight (TMA source, 128-byte aligned)
-  const size_t red_floats = (size_t)up(p.PS, 32) + (size_t)p.K1 * p.ldw1;
+  const size_t red_floats = (size_t)up(p.PS, 32) + (size_t)up((int64_t)p.K1 * p.ldw1, 32) + (size_t)((p.R + 7) & ~7) * p.ldu;
   VJF_CUDA_OK(cudaMalloc(&h->reduced, red_floats * sizeof(float)));
   VJF_CUDA_OK(cudaMemset(h->reduced, 0, red_floats * sizeof(float)));
   p.w1_mirror = h->reduced + up(p.PS, 32);
+  p.u_mirror = p.w1_mirror + up((int64_t)p.K1 * p.ldw1, 32);  // [roundup(R, 8)][ldu] row-padded copy of w_chol
   VJF_CUDA_OK(cudaMalloc(&h->sync_words, 64 * sizeof(unsigned)));
   VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
   p.partials = h->partials; p.reduced = h->reduced;

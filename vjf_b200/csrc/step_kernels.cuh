@@ -188,7 +188,8 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
 //   CX_TMA : recognition layer-1 weight + decoder staged by TMA bulk copies (waited just before they are needed, not at
 //            the start of the tile), and the observation tile of step t+1 prefetched (cp.async) at the end of the back
 //            half of step t, so that its HBM latency hides behind the reduction / barriers
-// mbarriers live in shared memory at s_flag + 2 (umma) and + 4 (weights); *_phase = parity to wait for.
+// mbarriers live in shared memory at s_flag + 2 (umma), + 4 (front weights: w_phase) and + 6 (back: w_chol / w_mean, y_phase);
+// *_phase = parity to wait for.
 #define CX_UMMA 1
 #define CX_TMA 2
 struct TileCtx { uint32_t tmem, umma_phase, w_phase, y_phase; int y_ready_t, flags, consts_staged; };
@@ -196,6 +197,9 @@ typedef TileCtx UmmaCtx;
 
 // bytes the front prologue moves by TMA
 static __device__ __forceinline__ uint32_t tma_head_bytes(const StepParams& p) { return 16u * (((uint32_t)p.H[p.L - 1] * p.d + 3u) >> 2); }
+static __device__ __forceinline__ uint32_t tma_back_bytes(const StepParams& p) {
+  return (p.U_in_smem ? (uint32_t)((p.R + 7) & ~7) * p.ldu * 4u : 0u) + 16u * (((uint32_t)p.R * p.d + 3u) >> 2);
+}
 static __device__ __forceinline__ uint32_t tma_front_bytes(const StepParams& p) {
   return (p.W1_in_smem ? (uint32_t)p.K1 * p.ldw1 * 4u : 0u) + (p.dec_in_smem ? (uint32_t)(p.d + 1) * p.D * 4u : 0u) + 2u * tma_head_bytes(p) +
          16u * (((uint32_t)p.d + 3u) >> 2);
@@ -488,8 +492,13 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   const float gam = st[p.lay.tr_logvar];
   const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
   if (part == PART_BACK) {
-    cp_async_wait_all();  // w_chol / w_mean staged by the back prologue
-    __syncthreads();
+    if (tma) {  // w_chol / w_mean: TMA bulk copies of the back prologue
+      mbar_wait(reinterpret_cast<uint64_t*>(sm + p.s_flag + 6), cx->y_phase);
+      cx->y_phase ^= 1u;
+    } else {
+      cp_async_wait_all();  // w_chol / w_mean staged by the back prologue
+      __syncthreads();
+    }
   }
   VJF_STAMP(p, t, 10);
   if (first && p.U_in_smem && t == 0) {  // is w_chol upper triangular?  Checked once per launch: every later w_chol is
@@ -739,7 +748,18 @@ static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what
       if (p.W1_in_smem) stage_async(sm + p.s_W1, p.ldw1, st + p.lay.mlp_w[0], p.H[0], p.K1, p.H[0], tid, VJF_NT);
     }
   }
-  if (what & STAGE_BACK) {
+  if ((what & STAGE_BACK) && tma) {
+    // w_chol from its row-padded mirror (kept current by the RLS commit; pads are zero) and w_mean: two TMA bulk copies,
+    // completion on the mbarrier the back half waits on
+    if (tid == 0) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + p.s_flag + 6);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, tma_back_bytes(p));
+      if (p.U_in_smem) tma_bulk_g2s(sm + p.s_U, p.u_mirror, (uint32_t)((p.R + 7) & ~7) * p.ldu * 4u, bar);
+      tma_bulk_g2s(sm + p.s_W, st + p.lay.w_mean, 16u * (((uint32_t)p.R * p.d + 3u) >> 2), bar);
+    }
+  } else if (what & STAGE_BACK) {
     stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
     if (p.U_in_smem) {
       float* U_s = sm + p.s_U;
@@ -953,7 +973,7 @@ __device__ __forceinline__ bool ldl_sweep_range(float (&v)[RPW][CPL], const int 
 
 template <int CPL, int RPW, int NW>
 static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv, int t,
-                                       double* resid_out) {
+                                       double* resid_out, const unsigned* wait_ctr = nullptr, unsigned wait_val = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, d = p.d, NR = 2 * R + d;
   // NW warps take part (row r lives in warp r % NW)
@@ -974,19 +994,18 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
   float v[RPW][CPL];
   float v0[PR][CPL];                            // P' rows kept for the commit
   float a_in[PR][CPL];                          // lower triangle of A (kept for the residual at the end)
-  // ---- issue every global load first (P rows, A rows, W, b), then compute ----
+  // ---- part 1, independent of this step's statistics (runs while the RLS CTA would otherwise wait for them): old P into
+  //      registers and shared memory, old W, and P W ----
 #pragma unroll
   for (int ri = 0; ri < PR; ++ri) {
     const int r = active_warp ? warp + NW * ri : (1 << 20);
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) {
       const int j = lane + 32 * ci;
-      const bool ok = (r < R) && (j < R);
-      v[ri][ci] = ok ? P[r * R + j] : 0.f;
-      a_in[ri][ci] = (ok && j <= r) ? A[r * R + j] : 0.f;
+      v[ri][ci] = ((r < R) && (j < R)) ? P[r * R + j] : 0.f;
     }
   }
-  for (int i = tid; i < R * d; i += VJF_NT) { Ws[i] = st[p.lay.w_mean + i]; bs[i] = bv[i]; }
+  for (int i = tid; i < R * d; i += VJF_NT) Ws[i] = st[p.lay.w_mean + i];
 #pragma unroll
   for (int ri = 0; ri < PR; ++ri) {
     const int r = active_warp ? warp + NW * ri : (1 << 20);
@@ -994,8 +1013,6 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     for (int ci = 0; ci < CPL; ++ci) {
       const int j = lane + 32 * ci;
       if (r < R && j < R) Qs[r * ldq + j] = v[ri][ci];
-      v[ri][ci] = fmaf(a_in[ri][ci], iv, v[ri][ci]);   // P' = P + A/v on and below the diagonal
-      v0[ri][ci] = v[ri][ci];
     }
   }
 #pragma unroll
@@ -1004,7 +1021,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     for (int ci = 0; ci < CPL; ++ci) v[ri][ci] = 0.f;
   if (tid == 0) misc[0] = 0.f;
   __syncthreads();
-  // g[r][c] = sum_j P[r][j] W[j][c] + b[r][c]/v   (old P, old W: module.py:93); one thread per output
+  // (P W)[r][c] (old P, old W: module.py:93); one thread per output, parked in zbuf across the wait
   for (int i = tid; i < R * d; i += VJF_NT) {
     const int r = i / d, c = i - r * d;
     float s0 = 0.f, s1 = 0.f;
@@ -1012,8 +1029,33 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     int j = 0;
     for (; j + 1 < R; j += 2) { s0 = fmaf(q[j], Ws[j * d + c], s0); s1 = fmaf(q[j + 1], Ws[(j + 1) * d + c], s1); }
     if (j < R) s0 = fmaf(q[j], Ws[j * d + c], s0);
-    zbuf[c * R + r] = fmaf(bs[i], iv, s0 + s1);
+    zbuf[c * R + r] = s0 + s1;
   }
+  // ---- part 2: this step's statistics.  P' = P + A/v on and below the diagonal ; g = P W + b/v ----
+  if (wait_ctr) wait_counter(wait_ctr, wait_val);
+  VJF_STAMP(p, t, 30);
+#pragma unroll
+  for (int ri = 0; ri < PR; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      a_in[ri][ci] = ((r < R) && (j < R) && j <= r) ? __ldcg(A + r * R + j) : 0.f;
+    }
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) {  // same thread <-> element mapping as above: no barrier needed in between
+    const int r = i / d, c = i - r * d;
+    const float b = __ldcg(bv + i);
+    bs[i] = b;
+    zbuf[c * R + r] = fmaf(b, iv, zbuf[c * R + r]);
+  }
+#pragma unroll
+  for (int ri = 0; ri < PR; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) {
+      v[ri][ci] = fmaf(a_in[ri][ci], iv, v[ri][ci]);
+      v0[ri][ci] = v[ri][ci];
+    }
   VJF_STAMP(p, t, 25);
   __syncthreads();
 #pragma unroll
@@ -1094,6 +1136,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
         const int c = r - R - d;
         const float uv = (j >= c) ? x : 0.f;
         Uout[c * R + j] = uv;
+        if (p.use_tma) p.u_mirror[c * p.ldu + j] = uv;  // row-padded mirror: the TMA source of the next back half
         Qs[c * ldq + j] = uv;
       }
     }
@@ -1198,6 +1241,7 @@ static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv,
     const float sd = sqrtf(dvec[c]);
     Lout[i] = (c < r) ? M[r * ldm + c] / sd : ((c == r) ? sd : 0.f);
     Uout[i] = (c >= r) ? M[(R + d + r) * ldm + c] / sd : 0.f;
+    if (p.use_tma) p.u_mirror[r * p.ldu + c] = Uout[i];
     const int lo = (c <= r) ? i : (c * R + r);
     Pout[i] = fmaf(A[lo], iv, P[lo]);
   }
@@ -1218,7 +1262,8 @@ static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv,
 }
 
 // finmask: bit0 recon finite, bit1 dyn finite, bit2 entropy finite (from the reduced sums)
-static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned finmask) {
+static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned finmask, const unsigned* wait_ctr = nullptr,
+                                unsigned wait_val = 0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, d = p.d;
   float* st = p.state;
@@ -1230,33 +1275,41 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   const bool warm = p.flags & VJF_FLAG_WARMUP;
   const bool upd = p.flags & VJF_FLAG_UPDATE;
 
-  if (p.world > 1) finmask = (isfinite(scal[SC_RECON]) ? 1u : 0u) | (isfinite(scal[SC_DYN]) ? 2u : 0u) | (isfinite(scal[SC_ENT]) ? 4u : 0u);
-  if (tid == 0 && !p.init_mode) {
-    unsigned stbits = 0;
-    float l_recon = scal[SC_RECON] / Bf, l_dyn = scal[SC_DYN] / Bf, h = scal[SC_ENT] / Bf;
-    if (!(finmask & 1u)) { l_recon = 0.f; stbits |= VJF_ST_RECON_NONFINITE; }
-    if (!(finmask & 2u)) { l_dyn = 0.f; stbits |= VJF_ST_DYN_NONFINITE; }
-    if (!(finmask & 4u)) { h = 0.f; stbits |= VJF_ST_ENTROPY_NONFINITE; }
-    if (scal[SC_BADMSE] != 0.f) stbits |= VJF_ST_MSE_NONFINITE;
-    float loss = l_recon - h;
-    if (!warm) loss += l_dyn;
-    if (p.losses) {
-      float* o = p.losses + (size_t)t * 4;
-      o[0] = loss; o[1] = -l_recon; o[2] = -l_dyn; o[3] = h;
+  // Overlapped Poisson schedule: the caller hands over the statistics-ready counter instead of waiting itself.  When the
+  // register factorisation runs, its statistics-independent part (old P, P W) is done first and the wait happens inside
+  // it; the loss sums (one thread, nothing waits for them) are then written after the factorisation.
+  const bool defer = wait_ctr && upd && !warm && p.R <= 128 && !p.init_mode && p.lik == VJF_LIK_POISSON;
+  if (wait_ctr && !defer) wait_counter(wait_ctr, wait_val);
+  auto losses_and_likelihood = [&]() {
+    if (p.world > 1) finmask = (isfinite(scal[SC_RECON]) ? 1u : 0u) | (isfinite(scal[SC_DYN]) ? 2u : 0u) | (isfinite(scal[SC_ENT]) ? 4u : 0u);
+    if (tid == 0 && !p.init_mode) {
+      unsigned stbits = 0;
+      float l_recon = scal[SC_RECON] / Bf, l_dyn = scal[SC_DYN] / Bf, h = scal[SC_ENT] / Bf;
+      if (!(finmask & 1u)) { l_recon = 0.f; stbits |= VJF_ST_RECON_NONFINITE; }
+      if (!(finmask & 2u)) { l_dyn = 0.f; stbits |= VJF_ST_DYN_NONFINITE; }
+      if (!(finmask & 4u)) { h = 0.f; stbits |= VJF_ST_ENTROPY_NONFINITE; }
+      if (scal[SC_BADMSE] != 0.f) stbits |= VJF_ST_MSE_NONFINITE;
+      float loss = l_recon - h;
+      if (!warm) loss += l_dyn;
+      if (p.losses) {
+        float* o = p.losses + (size_t)t * 4;
+        o[0] = loss; o[1] = -l_recon; o[2] = -l_dyn; o[3] = h;
+      }
+      if (stbits) atomicOr(p.status, stbits);
+      // GaussianLikelihood.update (vjf/likelihood.py:28-40): reads the post-SGD logvar
+      if (upd && p.lik == VJF_LIK_GAUSSIAN) {
+        const float mse = scal[SC_SSE] / (Bf * (float)p.D);
+        float n_new;
+        const float var = running_var_f(expf(st[p.lay.lik_logvar]), st[p.lay.lik_n], mse, Bf, 1000.f, &n_new);
+        st[p.lay.lik_logvar] = logf(var);
+        st[p.lay.lik_n] = n_new;
+      }
+      // overlapped schedule: the front half of step t+1 runs concurrently and needs this logvar for its decoder stage --
+      // publish "logvar of step t is final" (the trial CTAs wait for it there)
+      if (p.overlap && p.lik == VJF_LIK_GAUSSIAN) { __threadfence(); st_release_gpu_u32(p.ctrl + 4, (unsigned)(t + 1)); }
     }
-    if (stbits) atomicOr(p.status, stbits);
-    // GaussianLikelihood.update (vjf/likelihood.py:28-40): reads the post-SGD logvar
-    if (upd && p.lik == VJF_LIK_GAUSSIAN) {
-      const float mse = scal[SC_SSE] / (Bf * (float)p.D);
-      float n_new;
-      const float var = running_var_f(expf(st[p.lay.lik_logvar]), st[p.lay.lik_n], mse, Bf, 1000.f, &n_new);
-      st[p.lay.lik_logvar] = logf(var);
-      st[p.lay.lik_n] = n_new;
-    }
-    // overlapped schedule: the front half of step t+1 runs concurrently and needs this logvar for its decoder stage --
-    // publish "logvar of step t is final" (the trial CTAs wait for it there)
-    if (p.overlap && p.lik == VJF_LIK_GAUSSIAN) { __threadfence(); st_release_gpu_u32(p.ctrl + 4, (unsigned)(t + 1)); }
-  }
+  };
+  if (!defer) losses_and_likelihood();
   VJF_STAMP(p, t, 24);
   if (!upd) {
     if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
@@ -1275,15 +1328,16 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     const int nr8 = (2 * R + d + 7) / 8;  // rows per warp with 8 sweep warps
     (void)nr16;
     (void)nr8;
-    if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
-    else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
-    else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
-    else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
-    else if (R <= 128) { ok = rls_factor_regs<4, 17, 16>(p, sm, iv, A, bv, t, &resid); have_resid = ok; }
+    if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    else if (R <= 128) { ok = rls_factor_regs<4, 17, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
     else ok = rls_factor_smem(p, sm, iv, A, bv);
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
   }
+  if (defer) losses_and_likelihood();
   // every path (failed factorisation, shared-memory fallback, warm-up) ends with final RLS outputs here
   if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
 
