@@ -1280,9 +1280,9 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   // it; the loss sums (one thread, nothing waits for them) are then written after the factorisation.
   const bool defer = wait_ctr && upd && !warm && p.R <= 128 && !p.init_mode && p.lik == VJF_LIK_POISSON;
   if (wait_ctr && !defer) wait_counter(wait_ctr, wait_val);
-  auto losses_and_likelihood = [&]() {
+  auto losses_and_likelihood = [&](int who) {
     if (p.world > 1) finmask = (isfinite(scal[SC_RECON]) ? 1u : 0u) | (isfinite(scal[SC_DYN]) ? 2u : 0u) | (isfinite(scal[SC_ENT]) ? 4u : 0u);
-    if (tid == 0 && !p.init_mode) {
+    if (tid == who && !p.init_mode) {
       unsigned stbits = 0;
       float l_recon = scal[SC_RECON] / Bf, l_dyn = scal[SC_DYN] / Bf, h = scal[SC_ENT] / Bf;
       if (!(finmask & 1u)) { l_recon = 0.f; stbits |= VJF_ST_RECON_NONFINITE; }
@@ -1309,7 +1309,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
       if (p.overlap && p.lik == VJF_LIK_GAUSSIAN) { __threadfence(); st_release_gpu_u32(p.ctrl + 4, (unsigned)(t + 1)); }
     }
   };
-  if (!defer) losses_and_likelihood();
+  if (!defer) losses_and_likelihood(0);
   VJF_STAMP(p, t, 24);
   if (!upd) {
     if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
@@ -1337,7 +1337,6 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
   }
-  if (defer) losses_and_likelihood();
   // every path (failed factorisation, shared-memory fallback, warm-up) ends with final RLS outputs here
   if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
 
@@ -1373,6 +1372,8 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
       st[p.lay.tr_n] = n_new;
     }
   }
+  // deferred loss read-out: by a thread of another warp, concurrently with thread 0's state-noise update above
+  if (defer) losses_and_likelihood(32);
 }
 
 // finite flags of the three ELBO terms from the slots (every CTA evaluates this identically)
