@@ -47,7 +47,9 @@ print(f" timeline (us after step start; trial CTA {os.environ.get('PCTA', 1)}):"
 for n, i, dt in tl:
     a = s[5 + dt:-2 + dt if -2 + dt else None, i] - s[5:-2, 0]
     print(f"  {n:40s} {a.mean().item()/1e3:7.2f}")
-fine = [(13, 41, "decoder rows (warp 0)"), (41, 42, "decoder sync"), (42, 18, "decoder grads -> slot"),
+fine = [(10, 49, "S3 quadform (mma)"), (49, 50, "S3 p_mean dots"), (50, 51, "S3 sync"), (51, 15, "S3 p_logvar + sync"),
+        (17, 52, "wgrad: bias colsum"), (52, 53, "wgrad: fences + sync"), (53, 54, "wgrad: 12 tcgen05.mma + commit + wait"), (54, 43, "wgrad: TMEM -> slot epilogue"),
+        (13, 41, "decoder rows (warp 0)"), (41, 42, "decoder sync"), (42, 18, "decoder grads -> slot"),
         (17, 43, "colsum + umma wgrad"), (43, 44, "scalar warp sums + sync"), (44, 45, "scalar store + sync"), (45, 20, "y prefetch issue")]
 print(" fine stamps (trial CTA):")
 for i, j, n in fine:

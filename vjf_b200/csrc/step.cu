@@ -338,7 +338,7 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots, int pe
     static const bool no_tma = getenv("VJF_B200_NO_TMA") != nullptr;
     p.use_tma = (!no_tma && p.overlap && (p.D & 3) == 0 && (p.H[0] & 3) == 0 && ((p.H[p.L - 1] * p.d) & 3) == 0) ? 1 : 0;
     p.use_umma = (!no_umma && p.overlap && p.L == 1 && p.H[0] <= 64 && p.Gp >= 64 && p.W1_in_smem && nk <= 256 &&
-                  (size_t)p.K1 * p.ldw1 >= (size_t)2 * nk * rows) ? 1 : 0;
+                  (size_t)p.K1 * p.ldw1 >= (size_t)2 * nk * rows && (size_t)p.K1 * p.ldw1 >= 4 * 32 * 64 /* epilogue staging */) ? 1 : 0;
   }
   p.nslots = p.overlap ? p.ntiles + 1 : std::min(p.ntiles, max_slots + (persistent && max_slots < h->max_slots ? 1 : 0));
   return 0;

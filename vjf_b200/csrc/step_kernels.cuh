@@ -404,6 +404,8 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
           const float x = in_s[(4 * q + j) * K1p + k];
           if (p.in_split) { h[j] = x; l[j] = inl_s[(4 * q + j) * K1p + k]; }
           else { h[j] = tf32_hi(x); l[j] = x - h[j]; }
+          // a spare (zero-pad) input column becomes a column of ones: its product with g_pre is the bias gradient
+          if (k == NK - 1 && k >= K1) { h[j] = (4 * q + j < nb) ? 1.0f : 0.f; l[j] = 0.f; }
         }
         *reinterpret_cast<float4*>(bh + 4 * i) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(bl + 4 * i) = make_float4(l[0], l[1], l[2], l[3]);
@@ -530,15 +532,25 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       if (lane == 0) qp_s[b] = q;
     }
   }
-  for (int b = warp; b < nb; b += VJF_NWARP) {
-    for (int k = 0; k < d; ++k) {
-      float s = 0.f;
-      for (int r = lane; r < R; r += 32) s = fmaf(phi_s[b * Rp + r] + phil_s[b * Rp + r], W_s[r * d + k], s);
-      s = warp_sum(s);
-      if (lane == 0) pm_s[b * d + k] = xu_s[b * du + k] + s;
+  VJF_STAMP(p, t, 49);
+  for (int i = tid; i < nb * d; i += VJF_NT) {  // one thread per (trial, state dim): four independent chains of length R/4
+    const int b = i / d, k = i - b * d;
+    const float* ph = phi_s + b * Rp;
+    const float* pl = phil_s + b * Rp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < R; r += 4) {
+      s0 = fmaf(ph[r] + pl[r], W_s[r * d + k], s0);
+      s1 = fmaf(ph[r + 1] + pl[r + 1], W_s[(r + 1) * d + k], s1);
+      s2 = fmaf(ph[r + 2] + pl[r + 2], W_s[(r + 2) * d + k], s2);
+      s3 = fmaf(ph[r + 3] + pl[r + 3], W_s[(r + 3) * d + k], s3);
     }
+    for (; r < R; ++r) s0 = fmaf(ph[r] + pl[r], W_s[r * d + k], s0);
+    pm_s[i] = xu_s[b * du + k] + ((s0 + s1) + (s2 + s3));
   }
+  VJF_STAMP(p, t, 50);
   __syncthreads();
+  VJF_STAMP(p, t, 51);
   // p_logvar from the n-tile partial sums
   if (tid < nb) {
     float q = qp_s[tid];
@@ -622,14 +634,16 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     float* gcur = gpa; float* gnext = gpb; float* gcurl = gpal; float* gnextl = gpbl;
     if (uc) {
       // bias gradient = column sums of g_pre, then the weight gradient on tcgen05 / TMEM
-      if (tid < HL) {
+      const bool bias_col = p.umma_nk - 1 >= K1;  // the ones column exists: the bias gradient comes out of the MMA
+      if (!bias_col && tid < HL) {
         float s = 0.f;
         for (int b = 0; b < nb; ++b) { const int o = umma_canon(tid, b, 64); s += gpa[o] + gpal[o]; }
         acc_store(slot + p.lay.mlp_b[0] + tid, s, first);
       }
-      const float* bh = sm + p.s_W1;
+      float* bh = sm + p.s_W1;
       umma_wgrad(gpa, gpal, bh, bh + p.umma_nk * rows, p.umma_nk, K1, HL, rows, uc->tmem, 0u,
-                 reinterpret_cast<uint64_t*>(sm + p.s_flag + 2), uc->umma_phase, slot + p.lay.mlp_w[0], first);
+                 reinterpret_cast<uint64_t*>(sm + p.s_flag + 2), uc->umma_phase, slot + p.lay.mlp_w[0],
+                 bias_col ? slot + p.lay.mlp_b[0] : nullptr, bh, first, &p, t);
       uc->umma_phase ^= 1u;
       VJF_STAMP(p, t, 43);
     } else

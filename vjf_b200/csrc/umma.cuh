@@ -96,12 +96,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // One thread issues rows/8 k-steps x 3 MMAs (lo*hi, hi*lo, hi*hi) accumulating in TMEM columns [tcol, tcol + NK); 8 warps
 // then read the accumulator back (row n lives in TMEM lane n % 16 + 32 * (n / 16)) and store/add it to the slot.
 __device__ __forceinline__ void umma_wgrad(const float* gt_hi, const float* gt_lo, const float* inb_hi, const float* inb_lo, int NK, int K1, int H,
-                                           int rows, uint32_t tmem_base, uint32_t tcol, uint64_t* bar, uint32_t phase, float* dW, bool first) {
+                                           int rows, uint32_t tmem_base, uint32_t tcol, uint64_t* bar, uint32_t phase, float* dW, float* dB, float* stage,
+                                           bool first, const StepParams* sp = nullptr, int t = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // operands were written with ordinary shared-memory stores: make them visible to the async proxy, then hand over
+  if (sp) VJF_STAMP(*sp, t, 52);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (sp) VJF_STAMP(*sp, t, 53);
   if (tid == 0) {
     tc_fence_after();
     const uint32_t idesc = umma_idesc_tf32(64, NK);
@@ -119,20 +122,40 @@ __device__ __forceinline__ void umma_wgrad(const float* gt_hi, const float* gt_l
   }
   mbar_wait(bar, phase);
   tc_fence_after();
+  if (sp) VJF_STAMP(*sp, t, 54);
   // epilogue: a warp reaches the TMEM lanes of sub-partition q = warp % 4, which hold rows n = 16q .. 16q+15 in lanes
-  // 0..15 (M = 64 layout) ; the four warp groups split the 32-column chunks
+  // 0..15 (M = 64 layout).  The four warp groups take 32-column chunks; a chunk goes through shared memory (`stage`, the
+  // operand area the MMAs have finished reading) so that the slot is written with 128-bit stores of whole [k1][0..63] rows.
+  // Column NK-1 carries the bias gradient when `dB` is given (a row of ones in the B operand).
   {
-    const int q = warp & 3, grp = warp >> 2, n = 16 * q + lane;
-    for (int c0 = grp * 32; c0 < NK; c0 += 32 * (VJF_NT / 128)) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tcol + c0;
-      // the allocation is 256 columns wide, so a full 32-column read is always legal; columns >= K1 are not stored
-      float v[32];
-      tmem_ld32(taddr, v);
-      if (lane < 16 && n < H) {
+    const int q = warp & 3, grp = warp >> 2, n = 16 * q + lane, tg = tid & 127;
+    float* stg = stage + grp * (32 * 64);
+    for (int it = 0; it < 2; ++it) {
+      const int c0 = grp * 32 + it * 128;
+      if (c0 < NK) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + c0, v);
+        if (lane < 16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < K1) { float* o = dW + (size_t)(c0 + j) * H + n; if (first) *o = v[j]; else atomicAdd(o, v[j]); }
+          for (int j = 0; j < 32; ++j) stg[j * 64 + n] = v[j];
+        }
       }
+      __syncthreads();
+      if (c0 < NK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = tg + 128 * i, j = f >> 4, n4 = (f & 15) << 2, k1 = c0 + j;
+          if (n4 < H) {
+            const float4 val = *reinterpret_cast<const float4*>(stg + j * 64 + n4);
+            float* o = (k1 < K1) ? dW + (size_t)k1 * H + n4 : ((dB && k1 == NK - 1) ? dB + n4 : nullptr);
+            if (o) {
+              if (first) *reinterpret_cast<float4*>(o) = val;
+              else { atomicAdd(o, val.x); atomicAdd(o + 1, val.y); atomicAdd(o + 2, val.z); atomicAdd(o + 3, val.w); }
+            }
+          }
+        }
+      }
+      if (it == 0) __syncthreads();
     }
   }
   tc_fence_before();
