@@ -106,6 +106,30 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
 
 // Grid-wide barrier for the persistent (cooperatively launched) kernel.  `target` is a per-thread
 // running count of expected arrivals; the counter is zeroed by the host before each launch.
+// Grid barrier that also carries one bit of information per arriving CTA: the counter is 64 bits wide, arrivals count in the
+// low word, "my loss partials are not comfortably finite" arrivals in the high word (cumulative over the launch).  The
+// flag count is read with the same acquire load that observes the barrier, so the decision "take the exact finite
+// check this step" costs no extra L2 round trip.  Returns the cumulative flag count (identical on every CTA: the next
+// flagged arrival can only happen after every CTA has left this barrier and a later one).
+__device__ __forceinline__ unsigned grid_barrier_flag(unsigned long long* counter, unsigned& target, bool my_flag, unsigned* bcast) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    const unsigned long long inc = 1ull + (my_flag ? (1ull << 32) : 0ull);
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(inc) : "memory");
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+      if ((unsigned)v >= target) break;
+      __nanosleep(32);
+    }
+    *bcast = (unsigned)(v >> 32);
+    __threadfence();  // gpu-scope fence: also drops stale L1 lines before the CTA reads peers' data
+  }
+  __syncthreads();
+  return *bcast;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned nparticipants = 0) {
   __syncthreads();
   target += nparticipants ? nparticipants : gridDim.x;

@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned base_masks(const StepParams& p) {
 // serial factorisation of step t.
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float sm[];
-  unsigned target = 0, target2 = 0;
+  unsigned target = 0, target2 = 0, target1 = 0, nflag_seen = 0;
   bool back_staged = false;  // w_chol / w_mean of the coming back half already staged (issued behind the RLS tail)
   const bool trial_cta = blockIdx.x > 0;
   const bool early_rls = p.overlap && p.lik == VJF_LIK_POISSON;
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
     tc_fence_after();
     if (p.use_umma) ctx.tmem = *tslot;
   }
+  if (threadIdx.x == 0) *reinterpret_cast<int*>(sm + p.s_flag + 8) = 0;
   if (p.use_tma) {  // (re)build the row-padded mirror of the layer-1 weight; first read after the first grid barrier
     const int n = p.K1 * p.H[0];
     for (int i = blockIdx.x * VJF_NT + threadIdx.x; i < n; i += gridDim.x * VJF_NT) {
@@ -97,9 +98,15 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         phase_a_tile(p, sm, t, blockIdx.x - 1, true, masks, PART_BACK, cx);
       }
       VJF_STAMP(p, t, 1);
-      grid_barrier(p.barrier, target);
+      // barrier 1 also tells every CTA whether any CTA saw a loss partial that is not comfortably finite this attempt
+      int* nf = reinterpret_cast<int*>(sm + p.s_flag + 8);
+      const unsigned nflag = grid_barrier_flag(reinterpret_cast<unsigned long long*>(p.ctrl + 6), target1, *nf != 0,
+                                               reinterpret_cast<unsigned*>(sm + p.s_flag + 9));
+      if (threadIdx.x == 0) *nf = 0;
+      const bool suspicious = nflag != nflag_seen;
+      nflag_seen = nflag;
       VJF_STAMP(p, t, 2);
-      fin = (p.world > 1 || ld_acquire_u32(p.ctrl + 3) != (unsigned)(t + 1)) ? 7u : term_finite_mask(p, p.partials, gridDim.x, sm);  // sharded: decided on the global sums in B2
+      fin = (p.world > 1 || !suspicious) ? 7u : term_finite_mask(p, p.partials, gridDim.x, sm);  // sharded: decided on the global sums in B2
       // vjf/model.py:138-145: a non-finite term becomes the constant 0 => it must not contribute a
       // gradient either.  Rare; redo the trial-parallel phase with that term switched off.
       const unsigned nm = masks & (fin | ~7u);
@@ -285,7 +292,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_W1 = take(w1_in_smem ? (size_t)p.K1 * p.ldw1 : 0);
   p.s_hm = take((size_t)p.H[p.L - 1] * p.d);
   p.s_hv = take((size_t)p.H[p.L - 1] * p.d + p.d);
-  p.s_flag = take(8);  // [0] flag, [1] TMEM base, [2..7] three mbarriers
+  p.s_flag = take(12);  // [0] flag, [1] TMEM base, [2..7] three mbarriers, [8] non-finite partial seen, [9] barrier broadcast
   p.s_scf = take(VJF_NSCAL);
   p.s_b1 = take(2048 + 8);
   p.s_W = take((size_t)p.R * p.d);

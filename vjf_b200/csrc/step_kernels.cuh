@@ -690,8 +690,8 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     for (int w = 0; w < VJF_NWARP; ++w) s += red_s[w * VJF_NSCAL + tid];
     if (tid == 6) acc_store(slot + p.lay.lik_logvar, s, first);  // Gaussian d loss / d lambda (times B)
     else acc_store(slot + p.ps + tid, s, first);
-    // a loss-term partial that is not comfortably finite: tell the grid to take the exact (slow) check of the sums
-    if (tid < 3 && !(fabsf(s) < 1e30f)) atomicMax(p.ctrl + 3, (unsigned)(t + 1));
+    // a loss-term partial that is not comfortably finite: tell the grid (through barrier 1) to take the exact check of the sums
+    if (tid < 3 && !(fabsf(s) < 1e30f)) *reinterpret_cast<volatile int*>(sm + p.s_flag + 8) = 1;  // handed to barrier 1 (grid_barrier_flag)
   }
   __syncthreads();
   VJF_STAMP(p, t, 45);
