@@ -37,6 +37,12 @@ __device__ __forceinline__ unsigned base_masks(const StepParams& p) {
 //     front(0) ; T x { back(t) | bar | B1(t) | bar | { CTA 0: B2(t)  ||  trial CTAs: front(t+1) } | bar }
 // front(t+1) needs only the SGD-updated parameters (B1), not the RLS outputs, so it hides behind the
 // serial factorisation of step t.
+// RLS CTA, overlapped schedule: everything phase B2 of step t writes (state-noise logvar last) is final
+static __device__ __forceinline__ void publish_step_done(const StepParams& p, int t) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 3, (unsigned)(t + 1)); }
+}
+
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) float sm[];
   unsigned target = 0, target2 = 0, target1 = 0, nflag_seen = 0;
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         VJF_STAMP(p, t, 3);
         VJF_STAMP(p, t, 4);
         phase_b2(p, sm, t, fin, p.ctrl + 1, n_stat_chunks * (unsigned)(t + 1));
+        publish_step_done(p, t);
       }
     } else {
       phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x, gridDim.x, nullptr, epoch);
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       VJF_STAMP(p, t, 4);
       if (blockIdx.x == 0) {
         phase_b2(p, sm, t, fin);
+        if (p.overlap) publish_step_done(p, t);
       } else if (p.overlap && t + 1 < p.T) {
         phase_a_prologue(p, sm, STAGE_FRONT, cx);
         phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
@@ -161,7 +169,11 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
       }
     }
     VJF_STAMP(p, t, 5);
-    grid_barrier(p.barrier, target);
+    // Plain schedule: barrier 3 ends the step.  Overlapped schedule: nothing a trial CTA reads next is ordered by it any more
+    // (w_chol / w_mean: ctrl[5]; state-noise logvar: ctrl[3]; Gaussian likelihood logvar: ctrl[4]; the RLS CTA takes part in
+    // barrier 1 of the next step only after its tail, which orders the reuse of the reduced vector), so it is dropped and the
+    // back half of step t+1 starts while the RLS CTA is still in the residual / noise-variance tail of step t.
+    if (!p.overlap) grid_barrier(p.barrier, target);
     VJF_STAMP(p, t, 6);
   }
   if (cx && p.use_umma) {

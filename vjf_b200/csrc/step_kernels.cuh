@@ -491,8 +491,6 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   }
 
   // =============================== back half ===============================
-  const float gam = st[p.lay.tr_logvar];
-  const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
   if (part == PART_BACK) {
     if (tma) {  // w_chol / w_mean: TMA bulk copies of the back prologue
       mbar_wait(reinterpret_cast<uint64_t*>(sm + p.s_flag + 6), cx->y_phase);
@@ -560,6 +558,11 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   __syncthreads();
 
   VJF_STAMP(p, t, 15);
+  // state-noise logvar of the previous step.  Overlapped schedule: there is no grid barrier at the end of a step -- the RLS
+  // CTA publishes "step t-1 complete" (ctrl[3]) after its tail, and this is the first place that needs it
+  if (cx_overlap && t > 0) wait_counter(p.ctrl + 3, (unsigned)t);
+  const float gam = __ldcg(st + p.lay.tr_logvar);
+  const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
   // ---- S7: dynamics NLL (functional.py:55-75 via model.py:390-391), entropy (functional.py:25-29),
   //      g_mt and g_lt (times B) ----
   for (int i = tid; i < nb * d; i += VJF_NT) {
