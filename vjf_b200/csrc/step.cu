@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
   const unsigned n_stat_chunks = (unsigned)(((p.PS + 127) >> 7) - (p.pa >> 7));
   // Blackwell asynchronous machinery of the overlapped schedule (step_kernels.cuh, TileCtx): every trial CTA owns
   // 256 TMEM columns (tcgen05 weight gradient) and three mbarriers (tcgen05 commit, TMA weights, TMA observations)
-  TileCtx ctx{0u, 0u, 0u, 0u, -1, 0, 0};
+  TileCtx ctx{0u, 0u, 0u, 0u, -1, 0, 0, -1, 0};
   TileCtx* cx = nullptr;
   if (p.overlap && trial_cta && (p.use_umma || p.use_tma)) {
     cx = &ctx;
@@ -135,15 +135,44 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         phase_b1(p, sm, p.partials, gridDim.x, true, blockIdx.x - 1, gridDim.x - 1, p.ctrl + 1, epoch);
         VJF_STAMP(p, t, 3);
         VJF_STAMP(p, t, 23);
-        grid_barrier(p.ctrl + 2, target2, gridDim.x - 1);
+        // trial-only barrier; the Philox draw of step t+1 for this tile is computed by otherwise idle warps while
+        // thread 0 polls (noise depends on nothing but (seed, step, trial))
+        {
+          __syncthreads();
+          target2 += gridDim.x - 1;
+          if (threadIdx.x == 0) { __threadfence(); red_release_add_u32(p.ctrl + 2, 1u); }
+          if (cx && (cx->flags & CX_TMA) && !p.eps && t + 1 < p.T) {
+            const int b0 = (blockIdx.x - 1) * p.TB, nb = min(p.TB, p.B - b0), nblk = (p.d + 3) >> 2;
+            float* eps_s = sm + p.s_eps;
+            const int i = (int)threadIdx.x - 32;
+            if (i >= 0 && i < nb * 2 * nblk) {
+              const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
+              float z[4];
+              philox_normal4(p.seed, p.step0 + t + 1, p.trial_offset + b0 + b, which, blk, z);
+              for (int k = 0; k < 4; ++k)
+                if (blk * 4 + k < p.d) eps_s[b * 2 * p.d + which * p.d + blk * 4 + k] = z[k];
+            }
+            cx->eps_ready_t = t + 1;
+          }
+          if (threadIdx.x == 0) {
+            while (ld_acquire_u32(p.ctrl + 2) < target2) __nanosleep(32);
+            __threadfence();
+          }
+          __syncthreads();
+        }
         VJF_STAMP(p, t, 21);
         if (t + 1 < p.T) {
           phase_a_prologue(p, sm, STAGE_FRONT, cx);
           VJF_STAMP(p, t, 7);
+          if (cx) cx->early_ok = 1;
           phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
+          if (cx) cx->early_ok = 0;
           // w_chol / w_mean of step t are published before the RLS CTA finishes the step: stage them now, behind its tail
-          wait_counter(p.ctrl + 5, (unsigned)(t + 1));
-          phase_a_prologue(p, sm, STAGE_BACK, cx);
+          // (unless the front half found them published already and issued the copies itself)
+          if (!(cx && (cx->flags & CX_TMA) && *reinterpret_cast<volatile int*>(sm + p.s_flag + 10))) {
+            wait_counter(p.ctrl + 5, (unsigned)(t + 1));
+            phase_a_prologue(p, sm, STAGE_BACK, cx);
+          }
           back_staged = true;
         }
       } else {
@@ -162,9 +191,13 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_persistent_kernel(const __grid_
         if (p.overlap) publish_step_done(p, t);
       } else if (p.overlap && t + 1 < p.T) {
         phase_a_prologue(p, sm, STAGE_FRONT, cx);
+        if (cx) cx->early_ok = 1;
         phase_a_tile(p, sm, t + 1, blockIdx.x - 1, true, base_masks(p), PART_FRONT, cx);
-        wait_counter(p.ctrl + 5, (unsigned)(t + 1));
-        phase_a_prologue(p, sm, STAGE_BACK, cx);
+        if (cx) cx->early_ok = 0;
+        if (!(cx && (cx->flags & CX_TMA) && *reinterpret_cast<volatile int*>(sm + p.s_flag + 10))) {
+          wait_counter(p.ctrl + 5, (unsigned)(t + 1));
+          phase_a_prologue(p, sm, STAGE_BACK, cx);
+        }
         back_staged = true;
       }
     }

@@ -192,7 +192,7 @@ static __device__ __forceinline__ void decoder_stage(const StepParams& p, float*
 // *_phase = parity to wait for.
 #define CX_UMMA 1
 #define CX_TMA 2
-struct TileCtx { uint32_t tmem, umma_phase, w_phase, y_phase; int y_ready_t, flags, consts_staged; };
+struct TileCtx { uint32_t tmem, umma_phase, w_phase, y_phase; int y_ready_t, flags, consts_staged, eps_ready_t, early_ok; };
 typedef TileCtx UmmaCtx;
 
 // bytes the front prologue moves by TMA
@@ -203,6 +203,16 @@ static __device__ __forceinline__ uint32_t tma_back_bytes(const StepParams& p) {
 static __device__ __forceinline__ uint32_t tma_front_bytes(const StepParams& p) {
   return (p.W1_in_smem ? (uint32_t)p.K1 * p.ldw1 * 4u : 0u) + (p.dec_in_smem ? (uint32_t)(p.d + 1) * p.D * 4u : 0u) + 2u * tma_head_bytes(p) +
          16u * (((uint32_t)p.d + 3u) >> 2);
+}
+
+// one thread: w_chol (row-padded mirror, pads zero) and w_mean by TMA, completion on the mbarrier the back half waits on
+static __device__ __forceinline__ void issue_back_tma(const StepParams& p, float* sm) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + p.s_flag + 6);
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, tma_back_bytes(p));
+  if (p.U_in_smem) tma_bulk_g2s(sm + p.s_U, p.u_mirror, (uint32_t)((p.R + 7) & ~7) * p.ldu * 4u, bar);
+  tma_bulk_g2s(sm + p.s_W, p.state + p.lay.w_mean, 16u * (((uint32_t)p.R * p.d + 3u) >> 2), bar);
 }
 
 static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* sm, int t, int tile, bool first, unsigned masks, int part,
@@ -273,7 +283,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
             const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
             eps_s[i] = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d];
           }
-        } else {
+        } else if (cx->eps_ready_t != t) {  // (normally drawn during the trial-barrier wait, see draw_noise_tile)
           const int nblk = (d + 3) >> 2;
           for (int i = tid; i < nb * 2 * nblk; i += VJF_NT) {
             const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
@@ -441,6 +451,11 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     VJF_STAMP(p, t, 13);
     // ---- S5/S6: decoder eta = D xt + bias (model.py:29-30), likelihood terms, dloss/deta (times B), g_xt = g_eta D,
     //      decoder gradients.  Specialised on the state dimension so that xt and the accumulators live in registers.
+    // w_chol / w_mean of the previous step are usually published by the time the decoder stage is done (the RLS CTA is
+    // ahead): their TMA is then issued before the Gram stage (below), so that the copies land behind it instead of in
+    // front of the back half
+    const bool early_try = tma && part == PART_FRONT && t > 0 && cx->early_ok && tid == 0;
+    if (early_try) *reinterpret_cast<int*>(sm + p.s_flag + 10) = 0;
     // Gaussian likelihood: its logvar is updated by the RLS CTA (GaussianLikelihood.update) concurrently with this front
     // half in the overlapped schedule -- wait until the value of the previous step is final, then read it past L1
     float lam = 0.f;
@@ -459,6 +474,10 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     }
 
     VJF_STAMP(p, t, 18);
+    if (early_try && ld_acquire_u32(p.ctrl + 5) >= (unsigned)t) {  // published: the copies land behind the Gram stage
+      issue_back_tma(p, sm);
+      *reinterpret_cast<int*>(sm + p.s_flag + 10) = 1;
+    }
     // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
     mma_gram(phi_s, phil_s, Rp, R, rows, slot + p.pa, first);
     {
@@ -768,14 +787,7 @@ static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what
   if ((what & STAGE_BACK) && tma) {
     // w_chol from its row-padded mirror (kept current by the RLS commit; pads are zero) and w_mean: two TMA bulk copies,
     // completion on the mbarrier the back half waits on
-    if (tid == 0) {
-      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + p.s_flag + 6);
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, tma_back_bytes(p));
-      if (p.U_in_smem) tma_bulk_g2s(sm + p.s_U, p.u_mirror, (uint32_t)((p.R + 7) & ~7) * p.ldu * 4u, bar);
-      tma_bulk_g2s(sm + p.s_W, st + p.lay.w_mean, 16u * (((uint32_t)p.R * p.d + 3u) >> 2), bar);
-    }
+    if (tid == 0) issue_back_tma(p, sm);
   } else if (what & STAGE_BACK) {
     stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
     if (p.U_in_smem) {
