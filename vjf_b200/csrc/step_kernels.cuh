@@ -12,74 +12,14 @@
 #include "umma.cuh"
 
 // ------------------------------------------------------------------------------------------
-// tile GEMM helpers (SIMT fp32; rows is a multiple of 4, leading dimensions are multiples of 4)
+// slot accumulation helpers (the tile GEMMs live in mma.cuh / umma.cuh)
 // ------------------------------------------------------------------------------------------
-
-// out[b][n] = act(bias[n] + sum_k A[b][k] W[k][n])      A: smem, W: global [K][N]
-__device__ __forceinline__ void tile_linear_fwd(const float* A, int lda, int K, const float* W, const float* bias, int N,
-                                                float* out, int ldo, int rows, bool do_tanh) {
-  const int items = N * (rows >> 2);
-  for (int it = threadIdx.x; it < items; it += VJF_NT) {
-    const int n = it % N, b0 = (it / N) << 2;
-    const float bv = bias ? bias[n] : 0.0f;
-    float acc0 = bv, acc1 = bv, acc2 = bv, acc3 = bv;
-    const float* a0 = A + b0 * lda;
-    const float* a1 = a0 + lda;
-    const float* a2 = a1 + lda;
-    const float* a3 = a2 + lda;
-    const float* w = W + n;
-    int k = 0;
-    for (; k + 3 < K; k += 4) {
-      const float w0 = w[(size_t)k * N], w1 = w[(size_t)(k + 1) * N], w2 = w[(size_t)(k + 2) * N],
-                  w3 = w[(size_t)(k + 3) * N];
-      const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
-      const float4 x1 = *reinterpret_cast<const float4*>(a1 + k);
-      const float4 x2 = *reinterpret_cast<const float4*>(a2 + k);
-      const float4 x3 = *reinterpret_cast<const float4*>(a3 + k);
-      acc0 = fmaf(x0.x, w0, acc0); acc0 = fmaf(x0.y, w1, acc0); acc0 = fmaf(x0.z, w2, acc0); acc0 = fmaf(x0.w, w3, acc0);
-      acc1 = fmaf(x1.x, w0, acc1); acc1 = fmaf(x1.y, w1, acc1); acc1 = fmaf(x1.z, w2, acc1); acc1 = fmaf(x1.w, w3, acc1);
-      acc2 = fmaf(x2.x, w0, acc2); acc2 = fmaf(x2.y, w1, acc2); acc2 = fmaf(x2.z, w2, acc2); acc2 = fmaf(x2.w, w3, acc2);
-      acc3 = fmaf(x3.x, w0, acc3); acc3 = fmaf(x3.y, w1, acc3); acc3 = fmaf(x3.z, w2, acc3); acc3 = fmaf(x3.w, w3, acc3);
-    }
-    for (; k < K; ++k) {
-      const float wk = w[(size_t)k * N];
-      acc0 = fmaf(a0[k], wk, acc0); acc1 = fmaf(a1[k], wk, acc1); acc2 = fmaf(a2[k], wk, acc2); acc3 = fmaf(a3[k], wk, acc3);
-    }
-    if (do_tanh) { acc0 = tanhf(acc0); acc1 = tanhf(acc1); acc2 = tanhf(acc2); acc3 = tanhf(acc3); }
-    float* o = out + b0 * ldo + n;
-    o[0] = acc0; o[ldo] = acc1; o[2 * ldo] = acc2; o[3 * ldo] = acc3;
-  }
-}
 
 // A CTA's slot is written by that CTA only: the first tile stores, later tiles add with a fire-and-forget
 // reduction (same thread, same address => program order, so the sum order stays deterministic).
 __device__ __forceinline__ void acc_store(float* p, float v, bool first) {
   if (first) *p = v;
   else atomicAdd(p, v);
-}
-
-// dW[k][n] (+)= sum_b A[b][k] G[b][n]      A, G: smem; dW: this CTA's slot (global) [K][N]
-__device__ __forceinline__ void tile_wgrad(const float* A, int lda, int K, const float* G, int ldg, int N, int rows,
-                                           float* dW, bool first) {
-  const int kb = (K + 3) >> 2;
-  const int items = N * kb;
-  for (int it = threadIdx.x; it < items; it += VJF_NT) {
-    const int n = it % N, k0 = (it / N) << 2;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float* ap = A + k0;
-    const float* gp = G + n;
-#pragma unroll 4
-    for (int b = 0; b < rows; ++b) {
-      const float4 x = *reinterpret_cast<const float4*>(ap + b * lda);
-      const float g = gp[b * ldg];
-      a0 = fmaf(x.x, g, a0); a1 = fmaf(x.y, g, a1); a2 = fmaf(x.z, g, a2); a3 = fmaf(x.w, g, a3);
-    }
-    float* o = dW + (size_t)k0 * N + n;
-    acc_store(o, a0, first);
-    if (k0 + 1 < K) acc_store(o + N, a1, first);
-    if (k0 + 2 < K) acc_store(o + 2 * N, a2, first);
-    if (k0 + 3 < K) acc_store(o + 3 * N, a3, first);
-  }
 }
 
 // db[n] (+)= sum_b G[b][n]
