@@ -32,36 +32,64 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[64], likelihood="poisson",
           trials_per_gpu=4096, T=256)
+DATA_DESC = "synthetic (Lorenz-driven Poisson counts, random-init parameters; CPU-seeded, identical for both arms)"
 ALGO_BYTES_PER_TRIAL_STEP = lambda c, y_bytes=4: y_bytes * c["ydim"] + 4 * (c["udim"] + 4 * c["xdim"])
 
 
 # ------------------------------------------------------------------------------------------------
-def lorenz_poisson(T, B, D, seed, device=None):
+def lorenz_poisson(T, B, D, seed):
     """Synthetic data of SURVEY.md section 8d row C2: Lorenz (sigma=10, rho=28, beta=8/3, RK4 dt=0.01),
-    per-trial random initial state, z-scored; C ~ N(0,1)/sqrt(3), b=-1; y ~ Poisson(exp(xC+b))."""
+    per-trial random initial state, z-scored with the attractor's own moments; C ~ N(0,1)/sqrt(3), b=-1;
+    y ~ Poisson(exp(xC+b)).  Generated on the CPU from a seeded generator ONE TIME STEP AT A TIME, so that the first
+    T' < T steps of a longer run are the same tensors: the GPU arm (T = 256) and the CPU reference arm (a bounded
+    T-prefix) see identical observations."""
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(B, 3, generator=g, dtype=torch.float64) * 5 + torch.tensor([0., 0., 25.], dtype=torch.float64)
     C = (torch.randn(3, D, generator=g, dtype=torch.float64) / 3 ** 0.5)
-    if device is not None:
-        x, C = x.to(device), C.to(device)
 
     def f(s):
         return torch.stack((10 * (s[:, 1] - s[:, 0]), s[:, 0] * (28 - s[:, 2]) - s[:, 1], s[:, 0] * s[:, 1] - 8 / 3 * s[:, 2]), -1)
 
+    # fixed z-scoring constants (mean / std of the Lorenz attractor's coordinates) instead of statistics of the generated
+    # run, which would depend on T
+    mean = torch.tensor([0.0, 0.0, 23.55], dtype=torch.float64)
+    std = torch.tensor([7.92, 9.01, 8.62], dtype=torch.float64)
     dt, burn = 0.01, 200
-    xs = []
+    gy = torch.Generator(device="cpu").manual_seed(seed + 1)
+    y = torch.empty(T, B, D, dtype=torch.float32)
     for t in range(burn + T):
         k1 = f(x); k2 = f(x + 0.5 * dt * k1); k3 = f(x + 0.5 * dt * k2); k4 = f(x + dt * k3)
         x = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
         if t >= burn:
-            xs.append(x)
-    xs = torch.stack(xs)  # (T,B,3)
-    xs = (xs - xs.mean((0, 1))) / xs.std((0, 1))
-    rate = torch.exp(torch.clamp(xs @ C - 1.0, max=4.0))
-    gy = torch.Generator(device=rate.device).manual_seed(seed + 1)
-    y = torch.poisson(rate.float(), generator=gy)
-    return y  # float32 counts (T,B,D)
+            rate = torch.exp(torch.clamp(((x - mean) / std) @ C - 1.0, max=4.0)).float()
+            y[t - burn] = torch.poisson(rate, generator=gy)
+    return y  # float32 counts (T,B,D), CPU
+
+
+def bench_state(cfg, seed=1234):
+    """Initial parameters of the benchmark model in the reference's state_dict layout, drawn on the CPU with the
+    reference's distributions (nn.Linear default init, centroids U(-2,2), vjf/module.py:20) -- loaded into both arms."""
+    import math
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    D, d, u, R = cfg["ydim"], cfg["xdim"], cfg["udim"], cfg["n_rbf"]
+
+    def lin(out, inp, bias=True):
+        k = 1.0 / math.sqrt(inp)
+        w = (torch.rand(out, inp, generator=g) * 2 - 1) * k
+        b = (torch.rand(out, generator=g) * 2 - 1) * k if bias else None
+        return w, b
+    s = {}
+    n_in = D + u + 2 * d
+    for i, h in enumerate(cfg["hidden"]):
+        s[f"recognition.mlp.{2 * i}.weight"], s[f"recognition.mlp.{2 * i}.bias"] = lin(h, n_in)
+        n_in = h
+    s["recognition.mean.weight"], _ = lin(d, n_in, bias=False)
+    s["recognition.logvar.weight"], s["recognition.logvar.bias"] = lin(d, n_in)
+    s["decoder.decode.weight"], s["decoder.decode.bias"] = lin(D, d)
+    s["transition.velocity.feature.centroid"] = torch.rand(R, d + u, generator=g) * 4 - 2
+    return s
 
 
 class ClockSampler(threading.Thread):
@@ -128,7 +156,8 @@ def measured_peak_gbs():
 
 # ------------------------------------------------------------------------------------------------
 def cpu_port_rate(cfg, B, T_sample, seed=0, y=None):
-    """trial-steps/s of the numpy oracle (reference algorithm port) on a bounded sample."""
+    """trial-steps/s of the numpy oracle (reference algorithm port) on a bounded sample (fallback when the reference
+    package itself is not available)."""
     from oracle.vjf_oracle import OracleVJF
     rng = np.random.default_rng(seed)
     o = OracleVJF(cfg["ydim"], cfg["xdim"], cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], dtype=np.float32)
@@ -142,40 +171,144 @@ def cpu_port_rate(cfg, B, T_sample, seed=0, y=None):
     return B * T_sample / dt, dt
 
 
+class _Tape:
+    """Stands in for the NAME vjf.model.reparametrize (imported by name at vjf/model.py:18): reads N(0,1) draws from a
+    seeded tape instead of torch's global RNG; nothing else of the reference is touched."""
+
+    def __init__(self):
+        self.eps, self.i = None, 0
+
+    def load(self, eps):
+        self.eps, self.i = eps, 0
+
+    def __call__(self, q):
+        import torch
+        mean, logvar = q
+        e = self.eps[self.i]
+        self.i += 1
+        return mean + e * torch.exp(.5 * logvar)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+class ReferenceRunner:
+    """The UNMODIFIED reference (oracle/_ref/vjf, see oracle/make_ref.py): VJF.filter looped over a T-prefix of the
+    benchmark's own observations, from the benchmark's own initial parameters, fp32, all host threads."""
+
+    def __init__(self, cfg, B, T_s, ranks):
+        import torch
+        from oracle import make_ref
+        self.ref_model = make_ref.import_reference()
+        self.tape = _Tape()
+        self.ref_model.reparametrize = self.tape
+        torch.set_num_threads(os.cpu_count())
+        torch.set_default_dtype(torch.float32)
+        self.cfg, self.B, self.T_s = cfg, B, T_s
+        per = B // ranks
+        self.y = torch.cat([lorenz_poisson(T_s, per, cfg["ydim"], seed=1000 + r) for r in range(ranks)], 1)
+        g = torch.Generator().manual_seed(77)
+        self.eps = torch.randn(T_s, 2, B, cfg["xdim"], generator=g)
+        self.state = bench_state(cfg)
+
+    def fresh(self):
+        import torch
+        c = self.cfg
+        torch.manual_seed(0)
+        m = self.ref_model.VJF.make_model(c["ydim"], c["xdim"], c["udim"], c["n_rbf"], c["hidden"], c["likelihood"])
+        missing = m.load_state_dict(self.state, strict=False)
+        assert not missing.unexpected_keys, missing
+        return m
+
+    def epoch(self):
+        """T_s filter+learning steps from the initial state; returns seconds."""
+        m = self.fresh()
+        q = None
+        t0 = time.perf_counter()
+        for t in range(self.T_s):
+            self.tape.load(self.eps[t])
+            q, loss = m.filter(self.y[t], None, q, sgd=True, update=True, warm_up=False)
+        dt = time.perf_counter() - t0
+        self.last_loss = float(loss)
+        return dt
+
+    def describe(self, dt):
+        return (f"first {self.T_s} of the {self.cfg['T']} time steps x {self.B} trials ({dt:.1f} s), UNMODIFIED reference "
+                f"vjf.model.VJF.filter (oracle/_ref), fp32, torch {self._tv()} with {os.cpu_count()} threads on {cpu_model()}; "
+                f"same observations and initial parameters as the GPU arm, N(0,1) noise from a seeded tape")
+
+    @staticmethod
+    def _tv():
+        import torch
+        return torch.__version__
+
+
+def reference_available():
+    try:
+        from oracle import make_ref
+        make_ref.make()
+        return make_ref.available() or os.path.isdir(os.path.join(make_ref.REF_SRC, "vjf"))
+    except Exception:
+        return False
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     B = cfg["trials_per_gpu"] * args.gpus  # whole-job batch on the host cores
     cores = os.cpu_count()
-    T_s = max(1, args.ref_steps_per_step)
-    rng = np.random.default_rng(0)
-    y = rng.poisson(0.5, (T_s, B, cfg["ydim"])).astype(np.float32)
-    for _ in range(args.warmup):
-        cpu_port_rate(cfg, B, 1, y=y)
-    t0 = time.perf_counter()
-    rates = [cpu_port_rate(cfg, B, T_s, seed=i, y=y)[0] for i in range(args.steps)]
-    wall = time.perf_counter() - t0
-    val = float(np.mean(rates))
+    # the reference's (B,B) temporaries (vjf/module.py:76) make a step O(B^2): keep the sample bounded as the job grows
+    T_s = max(1, args.ref_steps_per_step // (args.gpus * args.gpus))
+    if reference_available():
+        rr = ReferenceRunner(cfg, B, T_s, args.gpus)
+        rr.T_s = 1
+        for _ in range(args.warmup):  # warm-up epochs of one time step each (thread pools, allocator)
+            rr.epoch()
+        rr.T_s = T_s
+        t0 = time.perf_counter()
+        dts = [rr.epoch() for _ in range(args.steps)]
+        wall = time.perf_counter() - t0
+        val = B * T_s * args.steps / sum(dts)
+        kind, sample = "reference", rr.describe(sum(dts))
+    else:
+        rng = np.random.default_rng(0)
+        y = rng.poisson(0.5, (T_s, B, cfg["ydim"])).astype(np.float32)
+        for _ in range(args.warmup):
+            cpu_port_rate(cfg, B, 1, y=y)
+        t0 = time.perf_counter()
+        rates = [cpu_port_rate(cfg, B, T_s, seed=i, y=y)[0] for i in range(args.steps)]
+        wall = time.perf_counter() - t0
+        val = float(np.mean(rates))
+        kind = "port"
+        sample = f"oracle/_ref ABSENT -> numpy/OpenBLAS oracle port of vjf/model.py:179-221; {T_s} time steps x {B} trials per bench step"
     out = {"impl": "reference", "metric": "trial-steps/sec", "value": val, "unit": "trial-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(cfg, args.gpus, T_override=T_s),
-           "cpu_baseline": {"value": val, "unit": "trial-steps/s", "cores": cores, "kind": "port",
-                            "sample": f"{T_s} time steps x {B} trials per bench step, numpy/OpenBLAS oracle port of vjf/model.py:179-221"},
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA_DESC,
+           "config": workload_config(cfg, args.gpus),
+           "cpu_baseline": {"value": val, "unit": "trial-steps/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": "trial-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
-def workload_config(cfg, n_gpus, T_override=None):
+def workload_config(cfg, n_gpus):
+    """Identical for both arms (the reference arm times a bounded T-prefix of this workload and says so in cpu_baseline.sample)."""
     return {"workload": f"{cfg['name']}: xdim={cfg['xdim']} ydim={cfg['ydim']} {cfg['likelihood']} n_rbf={cfg['n_rbf']} "
                         f"hidden={cfg['hidden']} trials={cfg['trials_per_gpu']}/GPU x {n_gpus} GPU, "
-                        f"T={T_override or cfg['T']} time steps per bench step (sgd=True, update=True, warm_up=False)",
+                        f"T={cfg['T']} time steps per bench step (sgd=True, update=True, warm_up=False)",
             "trials_per_gpu": cfg["trials_per_gpu"], "global_trials": cfg["trials_per_gpu"] * n_gpus,
-            "time_steps_per_step": T_override or cfg["T"], "parallelism": f"trial-sharded x{n_gpus}",
+            "time_steps_per_step": cfg["T"], "parallelism": f"trial-sharded x{n_gpus}",
             "l2_policy": "inputs larger than L2 (observations of one bench step = %.0f MB/GPU)" %
-                         (cfg["trials_per_gpu"] * (T_override or cfg["T"]) * cfg["ydim"] * 4 / 1e6)}
+                         (cfg["trials_per_gpu"] * cfg["T"] * cfg["ydim"] * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,10 +330,11 @@ def run_ours(args, cfg):
     B, T, D, d = cfg["trials_per_gpu"], cfg["T"], cfg["ydim"], cfg["xdim"]
     lib = _lib.load()
 
-    torch.manual_seed(1234)  # identical parameters on every rank
+    torch.manual_seed(1234)
     model = VJF.make_model(D, d, cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], max_trials=B, seed=99, device=dev)
-    y_dev = lorenz_poisson(T, B, D, seed=1000 + rank, device=dev).contiguous()
-    y_host = y_dev.cpu().pin_memory()
+    model.load_full_state(bench_state(cfg))  # identical parameters on every rank and in the reference arm
+    y_host = lorenz_poisson(T, B, D, seed=1000 + rank).contiguous().pin_memory()
+    y_dev = y_host.to(dev)
     mu_h = torch.empty(T, B, d).pin_memory(); lv_h = torch.empty(T, B, d).pin_memory(); ls_h = torch.empty(T, 4).pin_memory()
 
     # Every bench step is "the first epoch of a fit": it starts from the same initial parameters (a 70 KB
@@ -314,7 +448,7 @@ def run_ours(args, cfg):
         tps = measured_traffic_per_time_step() if (cfg["trials_per_gpu"] == C2["trials_per_gpu"] and world == 1) else None
         out = {"metric": "trial-steps/sec", "value": value, "unit": "trial-steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f32", "data": "synthetic (Lorenz-driven Poisson counts, random-init parameters)",
+               "vs_baseline": None, "dtype": "f32", "data": DATA_DESC,
                "config": workload_config(cfg, world),
                "us_per_time_step": total_ms / args.steps / T * 1e3,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -330,9 +464,16 @@ def run_ours(args, cfg):
         if e2e_u8:
             out["e2e_u8"] = e2e_u8
         if world == 1 and not args.no_cpu:
-            val, dt = cpu_port_rate(cfg, B, args.cpu_steps)
-            out["cpu_baseline"] = {"value": val, "unit": "trial-steps/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{args.cpu_steps} time steps x {B} trials ({dt:.1f} s), numpy/OpenBLAS oracle port of vjf/model.py:179-221"}
+            if reference_available():
+                rr = ReferenceRunner(cfg, B, args.cpu_steps, 1)
+                rr.epoch()  # warm-up (thread pools, allocator)
+                dt = rr.epoch()
+                out["cpu_baseline"] = {"value": B * args.cpu_steps / dt, "unit": "trial-steps/s", "cores": os.cpu_count(),
+                                       "kind": "reference", "sample": rr.describe(dt)}
+            else:
+                val, dt = cpu_port_rate(cfg, B, args.cpu_steps)
+                out["cpu_baseline"] = {"value": val, "unit": "trial-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"oracle/_ref ABSENT -> {args.cpu_steps} time steps x {B} trials ({dt:.1f} s), numpy/OpenBLAS oracle port of vjf/model.py:179-221"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -348,8 +489,8 @@ def main():
     ap.add_argument("--T", type=int, default=None, help="time steps per bench step (default 256)")
     ap.add_argument("--chunk", type=int, default=16, help="time steps per H2D chunk in the e2e path (the uint8 variant uses 2x)")
     ap.add_argument("--spinup", type=float, default=1.0, help="seconds of extra untimed load so clocks leave idle")
-    ap.add_argument("--cpu-steps", type=int, default=120, help="time steps of the CPU baseline sample (~10-20 s)")
-    ap.add_argument("--ref-steps-per-step", type=int, default=16, help="--impl reference: time steps per bench step")
+    ap.add_argument("--cpu-steps", type=int, default=24, help="time steps of the CPU baseline sample (~10-20 s of the reference)")
+    ap.add_argument("--ref-steps-per-step", type=int, default=8, help="--impl reference: time steps (a T-prefix of the workload) per bench step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     cfg = dict(C2)

@@ -90,6 +90,13 @@ def check(rc):
         raise RuntimeError("vjf_b200: " + load().vjf_last_error().decode())
 
 
+class DevBuf:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
 def make_config(ydim, xdim, udim, n_rbf, hidden_sizes, likelihood, max_trials):
     hs = list(hidden_sizes)
     if not 1 <= len(hs) <= MAX_LAYERS:

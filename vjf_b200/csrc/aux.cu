@@ -53,7 +53,7 @@ vjf_rls_stats_kernel(const __grid_constant__ StepParams p, const float* xs, cons
     }
     __syncthreads();
     float* Ap = slot + p.pa;
-    const int kb = Rp >> 2;
+    const int kb = (R + 3) >> 2;  // column blocks of 4 that hold at least one real column (phi rows are padded to Rp >= 4 kb)
     for (int it = tid; it < R * kb; it += VJF_NT) {
       const int kp = it % R, k0 = (it / R) << 2;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -120,11 +120,10 @@ extern "C" int vjf_rls_initialize(vjf_handle* h, int64_t N, const float* xs, con
     p.s_total = (int)std::max(std::max(off, b2), (size_t)1024);
     if ((size_t)p.s_total * 4 > h->smem_limit) { vjf_set_error("n_rbf=%d too large for this build", p.R); return -1; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->aux_attr_set) {  // per handle, i.e. per device
     VJF_CUDA_OK(cudaFuncSetAttribute(vjf_rls_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
     VJF_CUDA_OK(cudaFuncSetAttribute(vjf_rls_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
-    attr_set = true;
+    h->aux_attr_set = 1;
   }
   const int ntiles = (int)((N + VJF_TB_MAX - 1) / VJF_TB_MAX);
   p.nslots = std::min(ntiles, h->max_slots);
@@ -214,8 +213,16 @@ extern "C" int vjf_forecast(vjf_handle* h, int32_t n_step, int32_t B, float* x, 
   if (h->cfg.udim > 0 && !u) { vjf_set_error("udim=%d but u is NULL", h->cfg.udim); return -1; }
   const StepParams& p = h->base;
   cudaStream_t s = (cudaStream_t)stream;
-  float* w_all = nullptr;
-  VJF_CUDA_OK(cudaMallocAsync(&w_all, (size_t)n_step * p.R * p.d * sizeof(float), s));
+  // sampled weights of every step: a grow-only workspace owned by the handle (nothing is allocated per call once it is large enough)
+  const size_t need = (size_t)n_step * p.R * p.d * sizeof(float);
+  if (h->fc_w_sz < need) {
+    VJF_CUDA_OK(cudaStreamSynchronize(s));
+    if (h->fc_w) cudaFree(h->fc_w);
+    h->fc_w = nullptr; h->fc_w_sz = 0;
+    VJF_CUDA_OK(cudaMalloc(&h->fc_w, need));
+    h->fc_w_sz = need;
+  }
+  float* w_all = h->fc_w;
   vjf_forecast_weights_kernel<<<n_step, 256, 0, s>>>(h->state, p.lay, p.R, p.d, w_eps, w_all);
   const int wpb = 4;
   vjf_forecast_rollout_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(h->state, p.lay, p.R, p.d, p.u, n_step, B, x, u, w_all, x_eps);
@@ -226,6 +233,5 @@ extern "C" int vjf_forecast(vjf_handle* h, int32_t n_step, int32_t B, float* x, 
     ++g_vjf_launches;
   }
   VJF_CUDA_OK(cudaGetLastError());
-  VJF_CUDA_OK(cudaFreeAsync(w_all, s));
   return 0;
 }

@@ -229,11 +229,15 @@ __device__ __forceinline__ long long gtime_ns() {
 
 // development aid: thread 0 of CTA 0 (phase-A stage stamps 7..23: of the first trial CTA) drops a globaltimer
 // stamp into slot idx of step t (64 slots per step)
+#ifndef VJF_DEBUG_STAMPS
+#define VJF_STAMP(p, t, idx) do {} while (0)
+#else
 #define VJF_STAMP(p, t, idx)                                                              \
   do {                                                                                    \
     if ((p).dbg && threadIdx.x == 0 && blockIdx.x == (((p).overlap && (((idx) >= 7 && (idx) <= 23) || ((idx) >= 41 && (idx) <= 55))) ? (p).dbg_cta : 0)) \
       (p).dbg[(t) * 64 + (idx)] = gtime_ns();                                             \
   } while (0)
+#endif
 
 // clamp that propagates NaN the way torch.clamp does (fminf/fmaxf would drop it)
 __device__ __forceinline__ float clip1(float g) { return g < -1.0f ? -1.0f : (g > 1.0f ? 1.0f : g); }
@@ -263,6 +267,8 @@ struct vjf_handle {
   size_t stage_y_sz[2], stage_u_sz[2], stage_eps_sz[2], stage_mu_sz, stage_lv_sz, stage_loss_sz;
   cudaStream_t copy_stream, compute_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
+  int aux_attr_set;          // aux.cu kernels' shared-memory attribute set on this handle's device
+  float* fc_w; size_t fc_w_sz;  // forecast: sampled weights of every step (grow-only)
 };
 
 void vjf_set_error(const char* fmt, ...);

@@ -777,7 +777,7 @@ __device__ __forceinline__ bool sgd_applies(const StepParams& p, int e) {
 // end) are reduced first; when `signal` is given, every finished statistics chunk bumps it so that the RLS CTA
 // can start the factorisation without waiting for the gradient part.
 static __device__ void phase_b1(const StepParams& p, float* sm, const float* src, int nslots, bool apply, int cta, int nctas,
-                                unsigned* signal = nullptr, unsigned epoch = 0) {
+                                unsigned* signal = nullptr, unsigned epoch = 0, unsigned my_fin = 7u, unsigned need = 0u) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float invB = 1.0f / (float)p.Bglobal;
   float4* red = reinterpret_cast<float4*>(sm + p.s_b1);  // [16][32] float4
@@ -819,14 +819,25 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
         // the warp barrier orders every lane's stores before the flag lanes' st.release.sys (cumulativity): no separate
         // system-scope fence is needed, and it would cost a second NVLink round trip
         __syncwarp();
+        // The flag carries (epoch, finite mask of this rank's three ELBO sums): every CTA learns the global decision
+        // "a term is non-finite somewhere" from the flags it polls anyway, identically on every rank, before it applies
+        // the SGD step of its chunk (vjf/model.py:138-145, :212-214: such a step is skipped, as in the split path).
+        unsigned got = 7u;
         if (lane < p.world) {
-          st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[lane] + flag_off) + p.rank * nchx + ch, epoch);
+          st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[lane] + flag_off) + p.rank * nchx + ch, (epoch << 3) | (my_fin & 7u));
           const unsigned* wf = reinterpret_cast<const unsigned*>(p.peer[p.rank] + flag_off) + lane * nchx + ch;
           const long long t0 = clock64();
-          while (ld_acquire_sys_u32(wf) < epoch) {
-            if (clock64() - t0 > 6000000000ll) { atomicOr(p.status, (unsigned)VJF_ST_COMM_TIMEOUT); break; }  // ~3 s
+          unsigned v, spins = 0;
+          while (((v = ld_acquire_sys_u32(wf)) >> 3) < epoch) {
+            // a lost peer: give up after ~3 s, and at once when another CTA already gave up (sticky status bit)
+            if (clock64() - t0 > 6000000000ll) { atomicOr(p.status, (unsigned)VJF_ST_COMM_TIMEOUT); break; }
+            if ((++spins & 1023u) == 0 && (*reinterpret_cast<volatile unsigned*>(p.status) & VJF_ST_COMM_TIMEOUT)) break;
           }
+          got = ((v >> 3) >= epoch) ? (v & 7u) : 0u;
         }
+        got = __reduce_and_sync(0xffffffffu, got);
+        // after a time-out nothing is applied any more: the replicas would diverge silently (the host raises)
+        if ((got & need) != need || (*reinterpret_cast<volatile unsigned*>(p.status) & VJF_ST_COMM_TIMEOUT)) apply = false;
         __syncwarp();  // the polling lanes' ld.acquire.sys + this barrier order the inbox reads below after the peers' data
         if (e0 < p.PS) {
           t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -897,7 +908,9 @@ static __device__ double block_sum_d(double v, double* red) {
 // 1/sqrt(pivot_k) the three row groups hold chol(P'), (L^-1 g)^T and L^-T = w_chol.  Row r lives in warp
 // r % 16 (register slot r / 16), column j in lane j % 32 (slot j / 32): the sweep touches shared memory only
 // to broadcast the current column.  Returns false (block-uniform) if a pivot is not positive.
+#ifdef VJF_DEBUG_STAMPS
 __device__ long long g_sweep_ticks[160];  // development aid: clock64 at every column of the last sweep
+#endif
 
 // One range [k0, k1) of the LDL^T sweep with compile-time register slots: CN = slot of column k, CNP = slot of
 // column k + 1.  Multipliers of a warp's own rows come from a warp shuffle (element (r, k) lives in lane k % 32 of
@@ -910,7 +923,9 @@ __device__ __forceinline__ bool ldl_sweep_range(float (&v)[RPW][CPL], const int 
   for (int k = k0; k < k1; ++k) {
     const float* cb = colbuf + kb * NRP;
     float* cbn = colbuf + (kb ^ 1) * NRP;
+#ifdef VJF_DEBUG_STAMPS
     if (threadIdx.x == 0) g_sweep_ticks[k] = clock64();
+#endif
     const float piv = cb[k];
     float tk[RPW], cj[CPL];
 #pragma unroll
@@ -1242,7 +1257,8 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   const float* scal = red + p.ps;
   const float Bf = (float)p.Bglobal;
   const bool warm = p.flags & VJF_FLAG_WARMUP;
-  const bool upd = p.flags & VJF_FLAG_UPDATE;
+  bool upd = p.flags & VJF_FLAG_UPDATE;
+  if (p.world > 1 && (*reinterpret_cast<volatile unsigned*>(p.status) & VJF_ST_COMM_TIMEOUT)) upd = false;  // a peer was lost: commit nothing
 
   // Overlapped Poisson schedule: the caller hands over the statistics-ready counter instead of waiting itself.  When the
   // register factorisation runs, its statistics-independent part (old P, P W) is done first and the wait happens inside

@@ -18,11 +18,7 @@ from . import _lib
 from .model import VJF, Gaussian
 
 
-class _DevBuf:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+_DevBuf = _lib.DevBuf
 
 
 def shard_bounds(n_trials: int, world: int, rank: int):

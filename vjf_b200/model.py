@@ -321,6 +321,47 @@ class VJF(nn.Module):
         return mu, lv, losses
 
     @torch.no_grad()
+    def loss_gradients(self, y, u=None, qs: Gaussian = None, *, warm_up: bool = False, eps: Optional[Tensor] = None):
+        """Gradients of the step's loss w.r.t. every trainable tensor, BEFORE the clip (what autograd leaves in ``.grad``
+        after vjf/model.py:209), keyed like state_dict().  Runs the trial-parallel phase of the split step
+        (vjf_step_phase_a: forward + hand-derived backward + slot reduction) and reads the reduced sums; no parameter
+        is changed.  Returns (grads, Gaussian q_t)."""
+        y = self._coerce(y, "y")
+        B = y.shape[0]
+        u = self._coerce(u, "u") if (u is not None and self.udim > 0) else None
+        qm = ql = None
+        if qs is not None:
+            qm = qs.mean.detach().to(self.device, torch.float32).reshape(B, self.xdim).contiguous()
+            ql = qs.logvar.detach().to(self.device, torch.float32).reshape(B, self.xdim).contiguous()
+        if eps is not None:
+            eps = torch.as_tensor(eps).to(self.device, torch.float32).reshape(2, B, self.xdim).contiguous()
+        mean = torch.empty(B, self.xdim, dtype=torch.float32, device=self.device)
+        logvar = torch.empty_like(mean)
+        flags = self._flags(True, False, warm_up, qs is None)
+        lib = self._lib
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vjf_step_phase_a(self._h, B, B, _ptr(y), _lib.Y_F32, _ptr(u), _ptr(qm), _ptr(ql), _ptr(eps), self.seed,
+                                            self._step_index, 0, flags, _ptr(mean), _ptr(logvar), self._stream()))
+            n = int(lib.vjf_reduce_size(self._h))
+            red = torch.as_tensor(_lib.DevBuf(lib.vjf_reduce_buffer(self._h), n), device=self.device).clone()
+        red = red / B  # the slots hold sums over trials; the loss terms are batch means
+        L, d, D = self._lay, self.xdim, self.ydim
+        g = {}
+        n_in = D + self.udim + 2 * d
+        for i, hsz in enumerate(self.hidden_sizes):
+            g[f"recognition.mlp.{2 * i}.weight"] = red[L.mlp_w[i]:L.mlp_w[i] + n_in * hsz].view(n_in, hsz).t()
+            g[f"recognition.mlp.{2 * i}.bias"] = red[L.mlp_b[i]:L.mlp_b[i] + hsz]
+            n_in = hsz
+        g["recognition.mean.weight"] = red[L.head_m_w:L.head_m_w + n_in * d].view(n_in, d).t()
+        g["recognition.logvar.weight"] = red[L.head_v_w:L.head_v_w + n_in * d].view(n_in, d).t()
+        g["recognition.logvar.bias"] = red[L.head_v_b:L.head_v_b + d]
+        g["decoder.decode.weight"] = red[L.dec_w:L.dec_w + d * D].view(d, D).t()
+        g["decoder.decode.bias"] = red[L.dec_b:L.dec_b + D]
+        if self.likelihood_name == "gaussian":
+            g["likelihood.logvar"] = red[L.lik_logvar]
+        return g, Gaussian(mean, logvar)
+
+    @torch.no_grad()
     def fit(self, y, u=None, *, max_iter: int = 200, beta: float = 0.1, verbose: bool = False, rtol: float = 1e-4,
             progress: bool = True):
         """Same contract as the reference's VJF.fit (vjf/model.py:223-307): epochs over the sequence with a
