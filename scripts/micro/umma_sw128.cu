@@ -108,7 +108,7 @@ static size_t sw128_off(int row, int col, int rows) {
 }
 
 static int run(const char* name, const std::vector<float>& imgA, const std::vector<float>& imgB, Case c, const std::vector<double>& ref,
-               const std::vector<double>* ref2 = nullptr) {
+               const std::vector<double>* ref2 = nullptr, bool m64 = false) {
   float *dA, *dB, *dD;
   c.bytesA = (uint32_t)imgA.size() * 4; c.bytesB = (uint32_t)imgB.size() * 4;
   cudaMalloc(&dA, c.bytesA); cudaMalloc(&dB, c.bytesB); cudaMalloc(&dD, 128 * c.N * 4);
@@ -122,6 +122,7 @@ static int run(const char* name, const std::vector<float>& imgA, const std::vect
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
   double err = 0, mx = 0, err2 = 0;
   for (size_t i = 0; i < D.size(); ++i) {
+    if (m64 && ((i / c.N) & 31) >= 16) continue;  // M = 64: lanes 16..31 of every sub-partition hold no row
     err = fmax(err, fabs(ref[i] - D[i])); mx = fmax(mx, fabs(ref[i]));
     if (ref2) err2 = fmax(err2, fabs((*ref2)[i] - D[i]));
   }
@@ -196,6 +197,38 @@ int main() {
     c.idesc = make_idesc(M, N, 0, 1); c.nk = KB / 8; c.N = N;
     for (int s = 0; s < c.nk; ++s) { c.offA[s] = s * 32; c.offB[s] = s * 1024; }
     run(variant == 0 ? "case 4a: K x MN (N = 208), LBO = chunk stride, SBO = 1024" : "case 4b: K x MN (N = 208), LBO = 1024, SBO = chunk stride", ia, ib, c, ref);
+  }
+  // ---------------- case 5: A K-major SW128 [M x 32 trials] x B MN-major SWIZZLE_128B_BASE32B [32 trials][N columns] ----------------
+  // CUTLASS (sm100_common.inl): "for mn-major tf32 operands, SW128_32B is the only available smem layout": rows of 128 bytes,
+  // 32-byte pieces XOR-ed with (row % 4) (Swizzle<2,5,2> on the byte address), atoms of 4 rows.
+  for (int variant = 0; variant < 6; ++variant) {
+    const int Mv = (variant >= 4) ? 64 : 128;
+    const int N = (variant >= 4) ? 256 : 224, KB = 32;
+    std::vector<float> A(128 * KB, 0.f), G(KB * N);
+    for (int i = 0; i < Mv * KB; ++i) A[i] = tf32_trunc(rnd());
+    for (auto& v : G) v = tf32_trunc(rnd());
+    std::vector<float> ia(128 * KB), ib(KB * N);
+    for (int r = 0; r < 128; ++r) for (int kk = 0; kk < KB; ++kk) ia[sw128_off(r, kk, 128) / 4] = A[r * KB + kk];
+    for (int b = 0; b < KB; ++b) for (int n = 0; n < N; ++n) {
+      size_t off = ((size_t)(n >> 5) * KB + b) * 128 + (size_t)(n & 31) * 4;   // chunked rows of 128 bytes
+      off ^= (size_t)((b & 3) << 5);                                            // Swizzle<2,5,2>
+      ib[off / 4] = G[b * N + n];
+    }
+    std::vector<double> ref(128 * N, 0.0);
+    for (int m = 0; m < Mv; ++m) for (int n = 0; n < N; ++n) { double s2 = 0; for (int b = 0; b < KB; ++b) s2 += (double)A[m * KB + b] * G[b * N + n]; ref[(Mv == 64 ? (m % 16) + 32 * (m / 16) : m) * N + n] = s2; }
+    Case c{};
+    const uint32_t chunk = KB * 128;
+    c.descA = desc_fields(16, 1024, 2);
+    const int v4 = variant & 3;
+    c.descB = v4 == 0 ? desc_fields(chunk, 512, 1) : v4 == 1 ? desc_fields(512, chunk, 1) : v4 == 2 ? desc_fields(chunk, 1024, 1) : desc_fields(1024, chunk, 1);
+    c.idesc = make_idesc(Mv, N, 0, 1); c.nk = KB / 8; c.N = N;
+    for (int s2 = 0; s2 < c.nk; ++s2) { c.offA[s2] = s2 * 32; c.offB[s2] = s2 * 1024; }
+    char nm[128];
+    snprintf(nm, sizeof nm, "case 5.%d: M=%d K x MN(BASE32B) N=%d %s", variant, Mv, N,
+             v4 == 0 ? "LBO=chunk SBO=512" : v4 == 1 ? "LBO=512 SBO=chunk" : v4 == 2 ? "LBO=chunk SBO=1024" : "LBO=1024 SBO=chunk");
+    // M = 64: only TMEM lanes (m % 16) + 32 (m / 16) hold rows; compare those lanes only
+    if (Mv == 64) { /* other lanes of ref stay 0 and are compared against whatever TMEM holds: mask them */ }
+    run(nm, ia, ib, c, ref, nullptr, Mv == 64);
   }
   return 0;
 }
