@@ -169,6 +169,10 @@ int vjf_philox_normal(uint64_t seed, uint64_t step_index, uint64_t trial_offset,
 
 /* kernel-launch accounting for the benchmark (`gpu_launches`) */
 int64_t vjf_launch_count(void);
+/* which kernel ran the most recent vjf_run / vjf_step / vjf_run_sharded time loop: 1 = throughput tile pipeline (every
+ * contraction on tcgen05, observations by TMA tensor copies), 0 = the general persistent kernel (shapes outside the tile plan:
+ * several hidden layers, hidden width not a multiple of 32, uint8 observations, ...) */
+int32_t vjf_last_launch_kind(void);
 
 /* ---- whole-trajectory RLS re-initialisation: RBFDS.initialize + LinearRegression.initialize
  * (vjf/model.py:379-388, vjf/module.py:144-150).  xs, xt [N][xdim], u [N][udim] or NULL; the caller

@@ -15,7 +15,9 @@ def t_run(D, d, u, R, H, lik, B, T, reps=3):
         e0.record(); m.run(y, uu); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     st = m.status()
-    print(f"D={D} d={d} R={R} H={H} {lik} B={B} T={T}: {best/T*1e3:.2f} us/step  {B*T/best*1e3:.3e} trial-steps/s status={st}", flush=True)
+    from vjf_b200 import _lib
+    kind = _lib.load().vjf_last_launch_kind()
+    print(f"[kind {kind}] D={D} d={d} R={R} H={H} {lik} B={B} T={T}: {best/T*1e3:.2f} us/step  {B*T/best*1e3:.3e} trial-steps/s status={st}", flush=True)
 
 if __name__ == "__main__":
     t_run(200, 3, 0, 50, [64], "poisson", 4096, 64)

@@ -51,6 +51,7 @@ SIGNATURES = {
     "vjf_get_status": (C.c_int, [_P, _P, C.POINTER(_U32), _I32]),
     "vjf_philox_normal": (C.c_int, [_U64, _U64, _U64, _I32, _I32, _P, _P]),
     "vjf_launch_count": (_I64, []),
+    "vjf_last_launch_kind": (_I32, []),
     "vjf_rls_initialize": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "vjf_forecast": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vjf_kalman_predict_batched": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -64,7 +65,7 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get("VJF_B200_LIB") or _build.LIB  # VJF_B200_LIB: development builds (python -m vjf_b200.build --debug)
 
 
 def load(build_if_missing=True):

@@ -71,6 +71,31 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+DEBUG_SRCS = ("k_tile.cu", "step.cu")  # translation units that carry development stamps (-DVJF_DEBUG_STAMPS)
+LIB_DEBUG = os.path.join(LIBDIR, "libvjf_b200_dbg.so")
+
+
+def build_debug():
+    """Development library with globaltimer stamps in the tile pipeline: the release objects plus DEBUG_SRCS recompiled with
+    -DVJF_DEBUG_STAMPS, linked as lib/libvjf_b200_dbg.so (select it with VJF_B200_LIB=<path>)."""
+    build()
+    nvcc = _nvcc()
+    objs = []
+    for src in sources():
+        if src in DEBUG_SRCS:
+            o = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".dbg.o")
+            r = subprocess.run([nvcc] + NVCC_FLAGS + ["-DVJF_DEBUG_STAMPS", "-c", os.path.join(CSRC, src), "-o", o], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            objs.append(o)
+        else:
+            objs.append(_obj(src))
+    r = subprocess.run([nvcc] + LINK_FLAGS + objs + ["-o", LIB_DEBUG], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return LIB_DEBUG
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
@@ -99,4 +124,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build_debug())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

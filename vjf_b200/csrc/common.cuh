@@ -10,6 +10,7 @@
 #define VJF_NWARP (VJF_NT / 32)
 #define VJF_TB_MAX 32            // trials per tile (rows of the per-CTA tile)
 #define VJF_NSCAL 8              // scalar sums carried in the partial vector
+#define TK_NCW 15                // compute warps of the tile pipeline (warp 15 is its control warp)
 
 // scalar slots
 #define SC_RECON 0   // sum_b sum_j recon terms (without the 0.5*lambda*D constant)
@@ -24,7 +25,31 @@ struct Lay {  // int copies of vjf_layout (state buffers are < 2^31 floats)
   int prior_mean, prior_logvar, tr_logvar, centroid, logwidth, w_mean, w_chol, w_precision, w_pchol, lik_n, tr_n, total;
 };
 
+// Plan of the throughput tile pipeline (tile_kernels.cuh): tiles of TBR trials, every contraction on tcgen05 from
+// shared-memory images, observations streamed by TMA tensor copies.  Filled by the host (tile_host.cu).
+struct TilePlan {
+  int on;                    // this launch runs vjf_tile_kernel
+  int TBR, NBUF;             // trials per tile, observation buffers (double buffering)
+  int K1b, NCH, NCY;         // K1 + 1 (ones column = bias), 32-column chunks of the input image, chunks with observation columns
+  int Rk, NQ, PW, PWC;       // K of the quadratic form (roundup(R, 8)), N of QUAD / GRAM, phi image width (columns, chunks)
+  int HC, NBLK;              // H / 32, 128-row blocks of the layer-1 weight-gradient accumulator
+  int NS, SS;                // weight ring: stages, bytes per stage
+  int ukimg;                 // bytes of one image (hi or lo) of the [w_chol^T ; w_mean^T] operand
+  int RS;                    // row splits of the likelihood stage (warps per observation chunk)
+  // shared memory: byte offsets from the 1024-byte aligned base
+  int o_in[2], o_inlo, o_pg, o_ring, o_uk, o_f, scratch_bytes;
+  // float area: float offsets from o_f
+  int f_hs, ldhs, f_dec, f_hm, f_hv, f_cen, f_iw, f_ex, f_eps, f_xu, f_xt, f_mt, f_lt, f_pm, f_dx, f_gxt, f_gmt, f_glt, f_plv,
+      f_gxp, f_red, f_misc, f_bar, f_total;
+  int smem_bytes;
+  int c_d1, c_fl, c_gram, c_dw;  // tensor-memory columns of the accumulators
+};
+
 struct StepParams {
+  // ---- throughput tile pipeline ----
+  TilePlan tp;
+  float* w1k;   // recognition layer-1 weight as tcgen05 B-operand images (per 32-row chunk: hi | lo, K-major SW128), kept by the SGD step
+  float* uk;    // [w_chol^T ; w_mean^T] as B-operand images (hi | lo), kept by the RLS commit
   // ---- dimensions ----
   int B, Bglobal, D, d, u, R, L, H[VJF_MAX_LAYERS];
   int K1, K1p, E, du, Dp, Rp, Hp[VJF_MAX_LAYERS], Hpmax;
@@ -239,6 +264,27 @@ __device__ __forceinline__ long long gtime_ns() {
   } while (0)
 #endif
 
+// ---- operand images of the tile pipeline that the SGD step / RLS commit keep current (see tile_kernels.cuh) ----
+// The tensor core TRUNCATES fp32 operands to tf32 (profiles/micro_r02.txt), so an image holds the raw fp32 value as the
+// "hi" part and x - trunc(x) as the "lo" part.
+__device__ __forceinline__ float tf32_trunc_f(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// layer-1 weight element (input k, hidden unit n); bias row k = K1.  Chunk k / 32: [hi image | lo image], each [H rows][32 floats],
+// 16-byte pieces XOR (row % 8)
+__device__ __forceinline__ void w1k_store(const StepParams& p, int k, int n, float v) {
+  const int H = p.H[0], c = k >> 5, kk = k & 31;
+  float* base = p.w1k + (size_t)c * (2 * H * 32);
+  const int off = n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+  base[off] = v;
+  base[H * 32 + off] = v - tf32_trunc_f(v);
+}
+// element (row nq, contraction index r) of the [NQ][Rk] operand: rows < Rk hold w_chol^T, rows Rk.. hold w_mean^T
+__device__ __forceinline__ void uk_store(const StepParams& p, int nq, int r, float v) {
+  const int c = r >> 5, rr = r & 31;
+  const int off = (c * p.tp.NQ + nq) * 32 + ((((rr >> 2) ^ (nq & 7)) << 2) | (rr & 3));
+  p.uk[off] = v;
+  p.uk[(p.tp.ukimg >> 2) + off] = v - tf32_trunc_f(v);
+}
+
 // clamp that propagates NaN the way torch.clamp does (fminf/fmaxf would drop it)
 __device__ __forceinline__ float clip1(float g) { return g < -1.0f ? -1.0f : (g > 1.0f ? 1.0f : g); }
 
@@ -269,6 +315,7 @@ struct vjf_handle {
   cudaEvent_t ev_copied[2], ev_done[2];
   int aux_attr_set;          // aux.cu kernels' shared-memory attribute set on this handle's device
   float* fc_w; size_t fc_w_sz;  // forecast: sampled weights of every step (grow-only)
+  float* w1k; float* uk;         // operand images of the tile pipeline
 };
 
 void vjf_set_error(const char* fmt, ...);

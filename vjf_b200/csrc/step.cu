@@ -23,6 +23,8 @@ void vjf_set_error(const char* fmt, ...) {
 extern "C" const char* vjf_last_error(void) { return g_err; }
 extern "C" int vjf_version(void) { return 100; }
 extern "C" int64_t vjf_launch_count(void) { return g_vjf_launches; }
+static int g_vjf_last_kind = 0;
+extern "C" int32_t vjf_last_launch_kind(void) { return g_vjf_last_kind; }
 
 // ------------------------------------------------------------------------------------------
 // layout
@@ -252,13 +254,14 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
   p.partials = h->partials; p.reduced = h->reduced;
   p.barrier = h->sync_words; p.status = h->sync_words + 16; p.ctrl = h->sync_words + 32;
+  if (vjf_tile_create(h)) return -2;
   *out = h;
   return 0;
 }
 
 extern "C" int vjf_destroy(vjf_handle* h) {
   if (!h) return 0;
-  cudaFree(h->partials); cudaFree(h->reduced); cudaFree(h->sync_words);
+  cudaFree(h->partials); cudaFree(h->reduced); cudaFree(h->sync_words); cudaFree(h->w1k); cudaFree(h->uk);
   for (int r = 0; r < h->comm_world; ++r) if (r != h->comm_rank && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
   cudaFree(h->xbuf);
   for (int i = 0; i < 2; ++i) {
@@ -320,6 +323,17 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
   return 0;
 }
 
+// the throughput tile pipeline when the shapes are in its plan, else the persistent kernel of k_persistent.cu
+static int launch_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s) {
+  CUtensorMap map;
+  const int use_tile = vjf_tile_plan(h, p, p.y, p.y_dtype, T, B, &map);
+  if (use_tile < 0) return -2;
+  g_vjf_last_kind = use_tile ? 1 : 0;
+  if (use_tile) return vjf_tile_launch(h, p, map, s);
+  if (plan_tiles(h, p, B, h->max_slots, 1)) return -1;
+  return launch_persistent(h, p, s);
+}
+
 // development aid, debug builds only (python -m vjf_b200.build --debug): per-phase timestamps for the next launches
 static long long* g_dbg_ptr = nullptr;
 static int g_dbg_cta = 1;
@@ -334,16 +348,17 @@ extern "C" int vjf_run(vjf_handle* h, int32_t T, int32_t B, const void* y, int32
   if (check_ptrs(h, y, u, q0_mean, q0_logvar, flags, mu, logvar)) return -1;
   if (T < 1) { vjf_set_error("T must be >= 1"); return -1; }
   if (y_dtype != VJF_Y_F32 && y_dtype != VJF_Y_U8) { vjf_set_error("unknown y dtype"); return -1; }
+  if (B < 1 || B > h->cfg.max_trials) { vjf_set_error("trials B=%d outside [1, max_trials=%d]", B, h->cfg.max_trials); return -1; }
   StepParams p = h->base;
-  if (plan_tiles(h, p, B, h->max_slots, 1)) return -1;
   p.Bglobal = B;
   p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
   p.mu = mu; p.logvar = logvar; p.losses = losses;
   p.seed = seed; p.step0 = step0; p.trial_offset = 0; p.flags = flags; p.lr = lr; p.T = T;
   p.dbg = g_dbg_ptr;
   p.dbg_cta = g_dbg_cta;
-  return launch_persistent(h, p, (cudaStream_t)stream);
+  return launch_time_loop(h, p, T, B, (cudaStream_t)stream);
 }
+
 
 // ---- sharded run: exchange buffers over CUDA IPC ----
 static size_t xbuf_floats(const StepParams& p) { return (size_t)VJF_MAX_RANKS * 2 * ((p.PS + 127) & ~127); }
@@ -388,8 +403,8 @@ extern "C" int vjf_run_sharded(vjf_handle* h, int32_t T, int32_t B_local, int32_
   if (check_ptrs(h, y, u, q0_mean, q0_logvar, flags, mu, logvar)) return -1;
   if (h->comm_world < 1) { vjf_set_error("vjf_comm_connect has not been called"); return -1; }
   if (T < 1 || B_global < B_local) { vjf_set_error("bad T / batch sizes"); return -1; }
+  if (B_local < 1 || B_local > h->cfg.max_trials) { vjf_set_error("trials B=%d outside [1, max_trials=%d]", B_local, h->cfg.max_trials); return -1; }
   StepParams p = h->base;
-  if (plan_tiles(h, p, B_local, h->max_slots, 1)) return -1;
   p.Bglobal = B_global;
   p.y = y; p.y_dtype = y_dtype; p.u_in = u; p.q0m = q0_mean; p.q0l = q0_logvar; p.eps = eps;
   p.mu = mu; p.logvar = logvar; p.losses = losses;
@@ -397,7 +412,7 @@ extern "C" int vjf_run_sharded(vjf_handle* h, int32_t T, int32_t B_local, int32_
   p.world = h->comm_world; p.rank = h->comm_rank; p.PSx = (p.PS + 127) & ~127; p.epoch0 = h->comm_epoch;
   for (int r = 0; r < p.world; ++r) p.peer[r] = h->peer[r];
   h->comm_epoch += (unsigned)T;
-  return launch_persistent(h, p, (cudaStream_t)stream);
+  return launch_time_loop(h, p, T, B_local, (cudaStream_t)stream);
 }
 
 extern "C" int vjf_step(vjf_handle* h, int32_t B, const float* y, const float* u, const float* q_mean, const float* q_logvar,

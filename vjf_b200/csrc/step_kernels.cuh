@@ -861,6 +861,11 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
             const float v = p.state[e0 + i] - p.lr * clip1(tv[i] * invB);
             p.state[e0 + i] = v;
             if (mir) mir[i] = v;
+            if (p.tp.on) {  // tile pipeline: the layer-1 weight and bias live on as tcgen05 operand images
+              const int wi = e0 + i - p.lay.mlp_w[0], bi = e0 + i - p.lay.mlp_b[0];
+              if (wi >= 0 && wi < p.K1 * p.H[0]) w1k_store(p, wi / p.H[0], wi % p.H[0], v);
+              else if (bi >= 0 && bi < p.H[0]) w1k_store(p, p.K1, bi, v);
+            }
           }
       }
       }
@@ -1121,6 +1126,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
         const float uv = (j >= c) ? x : 0.f;
         Uout[c * R + j] = uv;
         if (p.use_tma) p.u_mirror[c * p.ldu + j] = uv;  // row-padded mirror: the TMA source of the next back half
+        if (p.tp.on) uk_store(p, j, c, uv);
         Qs[c * ldq + j] = uv;
       }
     }
@@ -1139,6 +1145,7 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     if (j < R) s0 = fmaf(q[j], z[j], s0);
     const float w = s0 + s1;
     Wout[i] = w; Ws[i] = w;
+    if (p.tp.on) uk_store(p, p.tp.Rk + k, c, w);
   }
   __syncthreads();
   // overlapped schedule: w_chol / w_mean of this step are final -- let the trial CTAs stage them for the back half of the
@@ -1226,6 +1233,7 @@ static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv,
     Lout[i] = (c < r) ? M[r * ldm + c] / sd : ((c == r) ? sd : 0.f);
     Uout[i] = (c >= r) ? M[(R + d + r) * ldm + c] / sd : 0.f;
     if (p.use_tma) p.u_mirror[r * p.ldu + c] = Uout[i];
+    if (p.tp.on) uk_store(p, c, r, Uout[i]);
     const int lo = (c <= r) ? i : (c * R + r);
     Pout[i] = fmaf(A[lo], iv, P[lo]);
   }
@@ -1240,6 +1248,7 @@ static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv,
     float s = 0.f;
     for (int k = r; k < R; ++k) s = fmaf(Uout[r * R + k], M[(R + c) * ldm + k], s);
     Wout[i] = s;
+    if (p.tp.on) uk_store(p, p.tp.Rk + c, r, s);
   }
   __syncthreads();
   return true;
