@@ -36,6 +36,7 @@ for i in range(18):
     v = (s[lo:hi, i] - base).mean().item() / 1e3
     print(f"  {i:2d} {names[i]:36s} {v:8.2f}  {'' if prev is None else f'+{v - prev:6.2f}'}")
     prev = v
+print(" LK detail (warp 0): " + " ".join(f"{(s[lo:hi, i] - s[lo:hi, 10]).mean().item() / 1e3:.2f}" for i in range(20, 32)))
 cn = {32: "step start (y TMA + ring prefill issued)", 33: "CX seen", 34: "FWD issued", 35: "CPHI seen", 36: "UK loaded", 37: "QUAD issued", 38: "CPHIT seen", 39: "GRAM issued",
       40: "CG seen", 41: "DW issued"}
 print(" control warp:")

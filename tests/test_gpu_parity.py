@@ -246,7 +246,10 @@ def test_run_host_equals_run(cuda_mod):
     # uint8 spike counts give the same result as their float32 copy
     c = cuda_mod.model_from_golden(g)
     mu8, lv8, _ = c.run(y.to(torch.uint8), None, None, eps=eps)
-    assert torch.equal(mu8, mu) and torch.equal(lv8, lv)
+    # (uint8 buffers run on the general persistent kernel, fp32 buffers of this shape on the tile pipeline: same numbers up to
+    # the summation order, not bit for bit)
+    assert_close(mu8.cpu().numpy(), mu.cpu().numpy(), 2e-5, 2e-6, "uint8 mu")
+    assert_close(lv8.cpu().numpy(), lv.cpu().numpy(), 2e-5, 2e-6, "uint8 logvar")
 
 
 @pytest.mark.parametrize("tag", ["f32"])

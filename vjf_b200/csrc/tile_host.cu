@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tile_plan.h"
 
 static inline int rup(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -39,7 +40,6 @@ static bool tile_static_dims(const StepParams& p, TilePlan& pl) {
   pl.NBLK = (pl.NCH + 3) / 4;
   pl.ukimg = ((pl.Rk + 31) / 32) * pl.NQ * 128;
   pl.SS = 2 * H * 128;
-  pl.NS = 3;
   if (pl.PWC > 4 || pl.NQ > 256 || pl.NCY > TK_NCW) return false;
   pl.c_d1 = 0; pl.c_fl = H; pl.c_gram = H + pl.NQ; pl.c_dw = H + 2 * pl.NQ;
   if (pl.c_dw + pl.NBLK * H > 512) return false;
@@ -73,9 +73,15 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   const int H = p.H[0], d = p.d, D = p.D;
   static const int force_tbr = getenv("VJF_B200_TILE_ROWS") ? atoi(getenv("VJF_B200_TILE_ROWS")) : 0;
   pl.TBR = force_tbr ? force_tbr : 32;
-  pl.NBUF = 2;
+  // one tile per trial CTA (latency regime): the second observation buffer would never be used -- its space goes to the
+  // weight ring instead (deeper prefetch of the layer-1 weight chunks)
+  const int ntiles = (B + pl.TBR - 1) / pl.TBR;
+  pl.NBUF = (ntiles <= h->max_slots - 1) ? 1 : 2;
   pl.RS = std::max(1, std::min(TK_NCW / pl.NCY, pl.TBR));
   const int TBR = pl.TBR, chunkB = TBR * 128;
+  static const int force_ns = getenv("VJF_B200_TILE_NS") ? atoi(getenv("VJF_B200_TILE_NS")) : 0;
+  const int ns_hi = force_ns ? force_ns : std::min(TK_MAXNS, pl.NCH);
+  for (pl.NS = ns_hi; pl.NS >= 2; --pl.NS) {
   int o = 0;
   pl.o_in[0] = o; o += pl.NCH * chunkB;
   pl.o_in[1] = o; o += (pl.NBUF > 1 ? pl.NCH * chunkB : 0);
@@ -100,13 +106,15 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   pl.f_xu = take(TBR * p.du);
   pl.f_xt = take(TBR * d); pl.f_mt = take(TBR * d); pl.f_lt = take(TBR * d); pl.f_pm = take(TBR * d); pl.f_dx = take(TBR * d);
   pl.f_gxt = take(TBR * d); pl.f_gmt = take(TBR * d); pl.f_glt = take(TBR * d); pl.f_plv = take(TBR);
-  pl.f_gxp = take(pl.NCY * TBR * d);
+  pl.f_gxp = take(pl.NCY * TBR * d + 4 * TBR);  // g_xt partials per observation chunk, then the partial sums of squares of the quadratic form
   pl.f_red = take(16 * VJF_NSCAL + 16);
   pl.f_misc = take(16);
   pl.f_bar = take(2 * 32);  // mbarriers (8 bytes each; the float area starts 16-byte aligned)
   pl.f_total = f;
   pl.smem_bytes = pl.o_f + f * 4 + 1024;  // + slack for the 1024-byte alignment of the base
-  if ((size_t)pl.smem_bytes > h->smem_limit) return 0;
+  if ((size_t)pl.smem_bytes <= h->smem_limit) break;
+  }
+  if (pl.NS < 2) return 0;
   // scratch of the per-step flush (register accumulators of 15 warps) and workspace of the shared phases B1 / B2
   const int DX = d <= 2 ? 2 : (d == 3 ? 3 : (d == 4 ? 4 : 8));
   const int flush_floats = TK_NCW * (DX + 1) * 32 + TK_NCW * 2 * pl.HC * DX * 32 + 16 * VJF_NSCAL + 16 + 16;

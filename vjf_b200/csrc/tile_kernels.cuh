@@ -21,10 +21,10 @@
 #include <cstdio>
 #include <cuda.h>
 #include "step_kernels.cuh"
+#include "tile_plan.h"
 
 #define TK_NCT (TK_NCW * 32)
 #define TK_CTRL 15
-#define TK_MAXNS 4
 
 // development aid (debug builds: VJF_B200_DEBUG=1 python -m vjf_b200.build): globaltimer stamps of one trial CTA, first tile of every step
 #ifdef VJF_DEBUG_STAMPS
@@ -48,7 +48,7 @@ __device__ __forceinline__ void tk_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (spins > (1u << 26)) { printf("vjf_tile_kernel: mbarrier @%u time-out (cta %d thread %d parity %u)\n", smem_u32(bar), (int)blockIdx.x, (int)threadIdx.x, parity); __trap(); }
+    if (spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ uint64_t tk_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
@@ -104,149 +104,188 @@ __device__ __forceinline__ void tk_permute_row(unsigned char* rowp, int row) {
 __device__ __forceinline__ int tk_tile_of(int j) { return (int)blockIdx.x - 1 + j * ((int)gridDim.x - 1); }
 
 // ------------------------------------------------------------------------------------------------------------------
-// control warp: one time step's worth of TMA / tcgen05 issue for the tiles of this CTA
+// control warp: one time step's worth of TMA / tcgen05 issue for the tiles of this CTA.
+// Every lane executes the same instruction stream with warp-uniform operands (made explicit with a broadcast shuffle: the
+// values arrive through a call boundary), and the asynchronous instructions themselves are predicated on elect.sync --
+// operands in uniform registers, no per-instruction broadcast loop.
 // ------------------------------------------------------------------------------------------------------------------
 struct TkCtl { uint32_t rp, rc, ukn; };  // weight-ring items produced / consumed, UK loads (kernel lifetime)
 
-static __device__ __forceinline__ void tk_issue_y(const StepParams& p, const CUtensorMap* ymap, unsigned char* sb, uint64_t* bars, int t, int tile, int buf) {
-  const TilePlan& pl = p.tp;
-  uint64_t* bar = &bars[BK_YFULL0 + buf];
-  mbar_expect_tx(bar, (uint32_t)pl.NCY * pl.TBR * 128u);
-  for (int c = 0; c < pl.NCY; ++c) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(sb + pl.o_in[buf] + c * pl.TBR * 128)), "l"(ymap), "r"(c * 32), "r"(tile * pl.TBR), "r"(t), "r"(smem_u32(bar)) : "memory");
-  }
+#define TK_UNI(x) __shfl_sync(0xffffffffu, (x), 0)
+__device__ __forceinline__ void tku_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-static __device__ __forceinline__ void tk_produce(const StepParams& p, unsigned char* sb, uint64_t* bars, uint32_t item, int chunk) {
-  const TilePlan& pl = p.tp;
-  const int s = item % pl.NS;
-  const uint32_t u = item / pl.NS;
-  if (u >= 1) tk_wait(&bars[BK_WEMPTY0 + s], (u - 1) & 1);
-  const uint32_t bytes = 2u * p.H[0] * 128u;
-  mbar_expect_tx(&bars[BK_WFULL0 + s], bytes);
-  tma_bulk_g2s(sb + pl.o_ring + s * pl.SS, p.w1k + (size_t)chunk * (2 * p.H[0] * 32), bytes, &bars[BK_WFULL0 + s]);
+__device__ __forceinline__ void tku_commit(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tku_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tku_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tku_tensor3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n\t}\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tku_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
 }
 
-static __device__ void tk_control_step(const StepParams& p, const CUtensorMap* ymap, unsigned char* sb, uint64_t* bars, uint32_t tmem, int t,
-                                       int ntl, uint32_t it0, TkCtl& cs) {
+struct TkU {  // warp-uniform state of the control warp
+  uint32_t sbase, bbase, tmem, rp, rc, rbase, rend;
+  int t, ntl;
+};
+
+static __device__ __forceinline__ void tku_issue_y(const StepParams& p, const CUtensorMap* ymap, const TkU& u, int tile, int buf) {
   const TilePlan& pl = p.tp;
-  const int lane = threadIdx.x & 31;
-  const int H = p.H[0], TBR = pl.TBR;
+  const uint32_t bar = u.bbase + 8 * (BK_YFULL0 + buf);
+  tku_expect(bar, (uint32_t)pl.NCY * pl.TBR * 128u);
+  #pragma unroll 1
+  for (int c = 0; c < pl.NCY; ++c) tku_tensor3d(u.sbase + pl.o_in[buf] + c * pl.TBR * 128, ymap, c * 32, tile * pl.TBR, u.t, bar);
+}
+static __device__ __forceinline__ void tku_produce(const StepParams& p, TkU& u) {
+  const TilePlan& pl = p.tp;
+  const uint32_t item = u.rp, s = item % pl.NS, use = item / pl.NS;
+  if (use >= 1) tku_wait(u.bbase + 8 * (BK_WEMPTY0 + s), (use - 1) & 1);
+  const uint32_t bytes = 2u * p.H[0] * 128u, bar = u.bbase + 8 * (BK_WFULL0 + s);
+  const int chunk = (int)((item - u.rbase) % pl.NCH);
+  tku_expect(bar, bytes);
+  tku_bulk(u.sbase + pl.o_ring + s * pl.SS, p.w1k + (size_t)chunk * (2 * p.H[0] * 32), bytes, bar);
+  ++u.rp;
+}
+
+static __device__ void tk_control_step(const StepParams& p, const CUtensorMap* ymap, unsigned char* sb, uint64_t* bars, uint32_t tmem_in, int t_in,
+                                       int ntl_in, uint32_t it0_in, TkCtl& cs) {
+  const TilePlan& pl = p.tp;
+  TkU u;
+  u.sbase = TK_UNI(smem_u32(sb)); u.bbase = TK_UNI(smem_u32(bars)); u.tmem = TK_UNI(tmem_in);
+  u.rp = TK_UNI(cs.rp); u.rc = TK_UNI(cs.rc);
+  u.t = TK_UNI(t_in); u.ntl = TK_UNI(ntl_in);
+  uint32_t ukn = TK_UNI(cs.ukn);
+  const uint32_t it0 = TK_UNI(it0_in);
+  const int H = p.H[0], TBR = pl.TBR, ntl = u.ntl, t = u.t;
   const uint32_t chunkB = (uint32_t)TBR * 128u;
-  const uint32_t sbase = smem_u32(sb);
   const uint32_t id_fwd = tk_idesc(128, H, 0, 0), id_quad = tk_idesc(128, pl.NQ, 0, 0), id_gram = tk_idesc(128, pl.NQ, 1, 1), id_dw = tk_idesc(128, H, 1, 1);
-  const uint32_t rend = cs.rc + (uint32_t)ntl * pl.NCH;
-  if (lane == 0) {
-    // the weight images were written by other CTAs through the generic proxy (ordered by the grid barrier / counters)
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-    for (int b = 0; b < pl.NBUF && b < ntl; ++b) tk_issue_y(p, ymap, sb, bars, t, tk_tile_of(b), (int)((it0 + b) % pl.NBUF));
-    while (cs.rp < rend && cs.rp < cs.rc + pl.NS) { tk_produce(p, sb, bars, cs.rp, (int)((cs.rp - (rend - (uint32_t)ntl * pl.NCH)) % pl.NCH)); ++cs.rp; }
-  }
-  const uint32_t rbase = rend - (uint32_t)ntl * pl.NCH;
+  u.rbase = u.rc;
+  u.rend = u.rc + (uint32_t)ntl * pl.NCH;
+  // the weight images were written by other CTAs through the generic proxy (ordered by the grid barrier / counters)
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  #pragma unroll 1
+  for (int b = 0; b < pl.NBUF && b < ntl; ++b) tku_issue_y(p, ymap, u, tk_tile_of(b), (int)((it0 + b) % pl.NBUF));
+#pragma unroll 1
+  while (u.rp < u.rend && u.rp < u.rc + pl.NS) tku_produce(p, u);
   TK_STAMP(p, t, 0, TK_CTRL * 32, 32);
+  #pragma unroll 1
   for (int j = 0; j < ntl; ++j) {
     const uint32_t it = it0 + j;
     const int buf = (int)(it % pl.NBUF);
     const uint32_t par = it & 1;
     // ---------------- FWD ----------------
-    tk_wait(&bars[BK_CX], par);
+    tku_wait(u.bbase + 8 * BK_CX, par);
     tc_fence_after();
     TK_STAMP(p, t, j, TK_CTRL * 32, 33);
-    if (lane == 0) {
-      for (int c = 0; c < pl.NCH; ++c) {
-        const int s = cs.rc % pl.NS;
-        tk_wait(&bars[BK_WFULL0 + s], (cs.rc / pl.NS) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = sbase + pl.o_in[buf] + c * chunkB, a_lo = sbase + pl.o_inlo + c * chunkB;
-        const uint32_t b_hi = sbase + pl.o_ring + s * pl.SS, b_lo = b_hi + H * 128;
-        const int nks = min(4, (pl.K1b - 32 * c + 7) >> 3);
-        for (int ks = 0; ks < nks; ++ks) {
-          umma_tf32_ss(tmem + pl.c_d1, tk_kmaj(a_lo + 32 * ks), tk_kmaj(b_hi + 32 * ks), id_fwd, (c | ks) ? 1u : 0u);
-          umma_tf32_ss(tmem + pl.c_d1, tk_kmaj(a_hi + 32 * ks), tk_kmaj(b_lo + 32 * ks), id_fwd, 1u);
-          umma_tf32_ss(tmem + pl.c_d1, tk_kmaj(a_hi + 32 * ks), tk_kmaj(b_hi + 32 * ks), id_fwd, 1u);
-        }
-        umma_commit(&bars[BK_WEMPTY0 + s]);
-        ++cs.rc;
-        if (cs.rp < rend) { tk_produce(p, sb, bars, cs.rp, (int)((cs.rp - rbase) % pl.NCH)); ++cs.rp; }
+    #pragma unroll 1
+    for (int c = 0; c < pl.NCH; ++c) {
+      const uint32_t s = u.rc % pl.NS;
+      tku_wait(u.bbase + 8 * (BK_WFULL0 + s), (u.rc / pl.NS) & 1);
+      tc_fence_after();
+      const uint64_t a_hi = tk_kmaj(u.sbase + pl.o_in[buf] + c * chunkB), a_lo = tk_kmaj(u.sbase + pl.o_inlo + c * chunkB);
+      const uint64_t b_hi = tk_kmaj(u.sbase + pl.o_ring + s * pl.SS), b_lo = tk_kmaj(u.sbase + pl.o_ring + s * pl.SS + H * 128);
+      const int nks = min(4, (pl.K1b - 32 * c + 7) >> 3);
+      #pragma unroll 1
+      for (int ks = 0; ks < nks; ++ks) {  // a k-step advances 32 bytes inside the 128-byte rows: +2 in the descriptor's address field
+        tku_mma(u.tmem + pl.c_d1, a_lo + 2 * ks, b_hi + 2 * ks, id_fwd, (c | ks) ? 1u : 0u);
+        tku_mma(u.tmem + pl.c_d1, a_hi + 2 * ks, b_lo + 2 * ks, id_fwd, 1u);
+        tku_mma(u.tmem + pl.c_d1, a_hi + 2 * ks, b_hi + 2 * ks, id_fwd, 1u);
       }
-      umma_commit(&bars[BK_D1]);
+      tku_commit(u.bbase + 8 * (BK_WEMPTY0 + s));
+      ++u.rc;
+      if (u.rp < u.rend) tku_produce(p, u);
     }
-    __syncwarp();
+    tku_commit(u.bbase + 8 * BK_D1);
     TK_STAMP(p, t, j, TK_CTRL * 32, 34);
     // ---------------- QUAD ----------------
-    tk_wait(&bars[BK_CPHI], par);
+    tku_wait(u.bbase + 8 * BK_CPHI, par);
     tc_fence_after();
     TK_STAMP(p, t, j, TK_CTRL * 32, 35);
-    if (lane == 0) {
-      if (j == 0) {
-        // [w_chol^T ; w_mean^T] of the previous step: final once the RLS CTA has published it
-        if (t > 0) { while (ld_acquire_u32(p.ctrl + 5) < (unsigned)t) __nanosleep(32); }
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        mbar_expect_tx(&bars[BK_UK], 2u * pl.ukimg);
-        tma_bulk_g2s(sb + pl.o_uk, p.uk, 2u * pl.ukimg, &bars[BK_UK]);
-        tk_wait(&bars[BK_UK], cs.ukn & 1);
-        ++cs.ukn;
-      }
-      TK_STAMP(p, t, j, TK_CTRL * 32, 36);
-      const uint32_t p_hi = sbase + pl.o_pg, p_lo = p_hi + pl.PWC * chunkB;
-      const uint32_t u_hi = sbase + pl.o_uk, u_lo = u_hi + pl.ukimg;
+    if (j == 0) {
+      // [w_chol^T ; w_mean^T] of the previous step: final once the RLS CTA has published it
+      if (t > 0) { while (ld_acquire_u32(p.ctrl + 5) < (unsigned)t) __nanosleep(32); }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      tku_expect(u.bbase + 8 * BK_UK, 2u * pl.ukimg);
+      tku_bulk(u.sbase + pl.o_uk, p.uk, 2u * pl.ukimg, u.bbase + 8 * BK_UK);
+      tku_wait(u.bbase + 8 * BK_UK, ukn & 1);
+      ++ukn;
+    }
+    TK_STAMP(p, t, j, TK_CTRL * 32, 36);
+    {
+      const uint32_t p_hi = u.sbase + pl.o_pg, p_lo = p_hi + pl.PWC * chunkB;
+      const uint32_t u_hi = u.sbase + pl.o_uk, u_lo = u_hi + pl.ukimg;
       const int nch = (pl.Rk + 31) >> 5;
+      #pragma unroll 1
       for (int ch = 0; ch < nch; ++ch) {
         const int nks = min(4, (pl.Rk - 32 * ch) >> 3);
+        const uint64_t ah = tk_kmaj(p_hi + ch * chunkB), al = tk_kmaj(p_lo + ch * chunkB);
+        const uint64_t bh = tk_kmaj(u_hi + ch * pl.NQ * 128), bl = tk_kmaj(u_lo + ch * pl.NQ * 128);
+        #pragma unroll 1
         for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t ao = ch * chunkB + 32 * ks, bo = ch * pl.NQ * 128 + 32 * ks;
-          umma_tf32_ss(tmem + pl.c_fl, tk_kmaj(p_lo + ao), tk_kmaj(u_hi + bo), id_quad, (ch | ks) ? 1u : 0u);
-          umma_tf32_ss(tmem + pl.c_fl, tk_kmaj(p_hi + ao), tk_kmaj(u_lo + bo), id_quad, 1u);
-          umma_tf32_ss(tmem + pl.c_fl, tk_kmaj(p_hi + ao), tk_kmaj(u_hi + bo), id_quad, 1u);
+          tku_mma(u.tmem + pl.c_fl, al + 2 * ks, bh + 2 * ks, id_quad, (ch | ks) ? 1u : 0u);
+          tku_mma(u.tmem + pl.c_fl, ah + 2 * ks, bl + 2 * ks, id_quad, 1u);
+          tku_mma(u.tmem + pl.c_fl, ah + 2 * ks, bh + 2 * ks, id_quad, 1u);
         }
       }
-      umma_commit(&bars[BK_FL]);
+      tku_commit(u.bbase + 8 * BK_FL);
     }
-    __syncwarp();
     TK_STAMP(p, t, j, TK_CTRL * 32, 37);
     // ---------------- GRAM ----------------
-    tk_wait(&bars[BK_CPHIT], par);
+    tku_wait(u.bbase + 8 * BK_CPHIT, par);
     tc_fence_after();
     TK_STAMP(p, t, j, TK_CTRL * 32, 38);
-    if (lane == 0) {
-      const uint32_t p_hi = sbase + pl.o_pg, p_lo = p_hi + pl.PWC * chunkB;
-      for (int ks = 0; ks < (TBR >> 3); ++ks) {
-        const uint64_t dh = tk_mnmaj(p_hi + ks * 1024, chunkB), dl = tk_mnmaj(p_lo + ks * 1024, chunkB);
-        umma_tf32_ss(tmem + pl.c_gram, dl, dh, id_gram, (j | ks) ? 1u : 0u);
-        umma_tf32_ss(tmem + pl.c_gram, dh, dl, id_gram, 1u);
-        umma_tf32_ss(tmem + pl.c_gram, dh, dh, id_gram, 1u);
+    {
+      const uint64_t dh = tk_mnmaj(u.sbase + pl.o_pg, chunkB), dl = tk_mnmaj(u.sbase + pl.o_pg + pl.PWC * chunkB, chunkB);
+      #pragma unroll 1
+      for (int ks = 0; ks < (TBR >> 3); ++ks) {  // a k-step = 8 trials = 1024 bytes: +64 in the address field
+        tku_mma(u.tmem + pl.c_gram, dl + 64 * ks, dh + 64 * ks, id_gram, (j | ks) ? 1u : 0u);
+        tku_mma(u.tmem + pl.c_gram, dh + 64 * ks, dl + 64 * ks, id_gram, 1u);
+        tku_mma(u.tmem + pl.c_gram, dh + 64 * ks, dh + 64 * ks, id_gram, 1u);
       }
-      umma_commit(&bars[BK_GRAM]);
+      tku_commit(u.bbase + 8 * BK_GRAM);
     }
-    __syncwarp();
     TK_STAMP(p, t, j, TK_CTRL * 32, 39);
     // ---------------- DW ----------------
-    tk_wait(&bars[BK_CG], par);
+    tku_wait(u.bbase + 8 * BK_CG, par);
     tc_fence_after();
     TK_STAMP(p, t, j, TK_CTRL * 32, 40);
-    if (lane == 0) {
-      const uint32_t g_hi = sbase + pl.o_pg, g_lo = g_hi + pl.HC * chunkB;
+    {
+      const uint64_t bh = tk_mnmaj(u.sbase + pl.o_pg, chunkB), bl = tk_mnmaj(u.sbase + pl.o_pg + pl.HC * chunkB, chunkB);
+      #pragma unroll 1
       for (int mb = 0; mb < pl.NBLK; ++mb) {
-        const uint32_t a_hi = sbase + pl.o_in[buf] + 4 * mb * chunkB, a_lo = sbase + pl.o_inlo + 4 * mb * chunkB;
-        const uint32_t d = tmem + pl.c_dw + mb * H;
+        const uint64_t ah = tk_mnmaj(u.sbase + pl.o_in[buf] + 4 * mb * chunkB, chunkB), al = tk_mnmaj(u.sbase + pl.o_inlo + 4 * mb * chunkB, chunkB);
+        const uint32_t d = u.tmem + pl.c_dw + mb * H;
+        #pragma unroll 1
         for (int ks = 0; ks < (TBR >> 3); ++ks) {
-          const uint64_t ah = tk_mnmaj(a_hi + ks * 1024, chunkB), al = tk_mnmaj(a_lo + ks * 1024, chunkB);
-          const uint64_t bh = tk_mnmaj(g_hi + ks * 1024, chunkB), bl = tk_mnmaj(g_lo + ks * 1024, chunkB);
-          umma_tf32_ss(d, al, bh, id_dw, (j | ks) ? 1u : 0u);
-          umma_tf32_ss(d, ah, bl, id_dw, 1u);
-          umma_tf32_ss(d, ah, bh, id_dw, 1u);
+          tku_mma(d, al + 64 * ks, bh + 64 * ks, id_dw, (j | ks) ? 1u : 0u);
+          tku_mma(d, ah + 64 * ks, bl + 64 * ks, id_dw, 1u);
+          tku_mma(d, ah + 64 * ks, bh + 64 * ks, id_dw, 1u);
         }
       }
-      umma_commit(&bars[BK_DW]);
+      tku_commit(u.bbase + 8 * BK_DW);
       TK_STAMP(p, t, j, TK_CTRL * 32, 41);
       // the input buffer is free once these MMAs are done: observations of the tile after next
       if (j + pl.NBUF < ntl) {
-        tk_wait(&bars[BK_DW], par);
-        tk_issue_y(p, ymap, sb, bars, t, tk_tile_of(j + pl.NBUF), buf);
+        tku_wait(u.bbase + 8 * BK_DW, par);
+        tku_issue_y(p, ymap, u, tk_tile_of(j + pl.NBUF), buf);
       }
     }
-    __syncwarp();
   }
+  cs.rp = u.rp; cs.rc = u.rc; cs.ukn = ukn;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -259,6 +298,86 @@ struct TkAcc {
   float ghvb;                  // logvar-head bias gradient (threads ctid < d)
   float sc[VJF_NSCAL];
 };
+
+// tanh from one exponential: |abs err| < 1.5e-7 (the cancellation in t - 1 for small x costs relative, not absolute accuracy)
+__device__ __forceinline__ float tk_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  const float t = __expf(2.0f * xc);
+  const float r = __fdividef(t - 1.0f, t + 1.0f);
+  return (x != x) ? x : r;
+}
+
+#define TK_LK_RB 4  // rows per batch of the likelihood stage (independent chains in flight per warp)
+
+// Likelihood stage of one warp: observation chunk cy (a lane owns one column), trials rs, rs + RS, ...  TK_LK_RB trials are in
+// flight together; the row code is branch-free (selects) so that their chains interleave.
+template <int DX, int LIK>
+static __device__ __forceinline__ void tk_lk_rows(const StepParams& p, TkAcc<DX>& acc, const unsigned char* in_b, const float* xt_s, float* gxp_s,
+                                                   const float* dec, int cy, int rs, int nb, bool r_on, float lam, float e_nlam, float p_lam) {
+  const TilePlan& pl = p.tp;
+  const int lane = threadIdx.x & 31, d = p.d, D = p.D, TBR = pl.TBR;
+  const int jcol = 32 * cy + lane;
+  const bool jok = jcol < D;
+  float w[DX];
+  const float bj = jok ? dec[d * D + jcol] : 0.f;
+#pragma unroll
+  for (int k = 0; k < DX; ++k) w[k] = (jok && (DX == d || k < d)) ? dec[k * D + jcol] : 0.f;
+#pragma unroll 1
+  for (int bb = rs; bb < nb; bb += TK_LK_RB * pl.RS) {
+    float gx[TK_LK_RB][DX];
+#pragma unroll
+    for (int q = 0; q < TK_LK_RB; ++q) {
+      const int b = bb + q * pl.RS;
+      const bool on = jok && b < nb;
+      const int bc = min(b, nb - 1);  // loads of a masked row stay in range
+      float xt[DX], eta = bj;
+#pragma unroll
+      for (int k = 0; k < DX; ++k) { xt[k] = (DX == d || k < d) ? xt_s[bc * d + k] : 0.f; eta = fmaf(w[k], xt[k], eta); }
+      const float yv = *reinterpret_cast<const float*>(in_b + b32_off(bc, jcol, TBR));
+      float g;
+      if (LIK == VJF_LIK_GAUSSIAN) {
+        // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
+        const float r = yv - eta;
+        const float rsd = yv * p_lam - eta * p_lam;
+        const float mse = rsd * rsd;
+        acc.sc[SC_BADMSE] += (on && !isfinite(mse)) ? 1.f : 0.f;
+        acc.sc[SC_RECON] += on ? 0.5f * (mse + lam) : 0.f;
+        acc.sc[SC_SSE] += on ? r * r : 0.f;
+        g = -r * e_nlam;
+        acc.sc[6] += (on && r_on) ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
+      } else {
+        // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62; NaN propagates like torch.clamp
+        const float ec = fminf(eta, 10.0f);
+        const float ex = __expf(ec);
+        const bool isn = eta != eta;
+        acc.sc[SC_RECON] += on ? (isn ? eta : ex - yv * ec) : 0.f;
+        g = isn ? eta : ((eta <= 10.0f) ? (ex - yv) : 0.f);
+      }
+      g = (on && r_on) ? g : 0.f;
+      acc.gdb += g;
+#pragma unroll
+      for (int k = 0; k < DX; ++k) { acc.gdw[k] = fmaf(g, xt[k], acc.gdw[k]); gx[q][k] = g * w[k]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < TK_LK_RB; ++q)
+#pragma unroll
+        for (int k = 0; k < DX; ++k) gx[q][k] += __shfl_xor_sync(0xffffffffu, gx[q][k], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < TK_LK_RB; ++q) {
+        const int b = bb + q * pl.RS;
+        if (b < nb) {
+#pragma unroll
+          for (int k = 0; k < DX; ++k)
+            if (DX == d || k < d) gxp_s[(cy * TBR + b) * d + k] = gx[q][k];
+        }
+      }
+    }
+  }
+}
+
 
 template <int DX>
 static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, uint64_t* bars, uint32_t tmem, int t, int tile, uint32_t it,
@@ -283,46 +402,47 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
   const bool r_on = masks & 1u, d_on = masks & 2u, h_on = masks & 4u;
   const int ldhs = pl.ldhs;
 
-  // ---- A1: previous posterior, control input, noise; xs = m_s + eps1 exp(l_s / 2) (vjf/util.py:11-13); RBF features ----
-  {
   TK_STAMP(p, t, j, 0, 0);
+  // ---- A1: previous posterior, control input, noise; xs = m_s + eps1 exp(l_s / 2) (vjf/util.py:11-13) ----
+  {
     const size_t row0 = (size_t)t * p.B + b0;
     const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
     const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
     const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-    for (int i = ctid; i < TBR * E; i += TK_NCT) {
-      const int b = i / E, e = i - b * E;
-      float v = 0.f;
+    // one thread per (trial, state dimension): its four inputs are independent loads
+    #pragma unroll 1
+    for (int i = ctid; i < TBR * d; i += TK_NCT) {
+      const int b = i / d, k = i - b * d;
+      float ms = 0.f, ls = 0.f, e1 = 0.f, e2 = 0.f;
       if (b < nb) {
-        if (e < u) v = p.u_in[(row0 + b) * u + e];
-        else if (e < u + d) v = prior ? st[p.lay.prior_mean + e - u] : qm[(size_t)(b0 + b) * d + e - u];
-        else v = prior ? st[p.lay.prior_logvar + e - u - d] : ql[(size_t)(b0 + b) * d + e - u - d];
+        if (prior) { ms = st[p.lay.prior_mean + k]; ls = st[p.lay.prior_logvar + k]; }
+        else { ms = qm[(size_t)(b0 + b) * d + k]; ls = ql[(size_t)(b0 + b) * d + k]; }
+        if (p.eps) {
+          const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d;
+          e1 = e0[k]; e2 = e0[(size_t)p.B * d + k];
+        } else if ((k & 3) == 0) {
+          float z1[4], z2[4];
+          philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, 0, k >> 2, z1);
+          philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, 1, k >> 2, z2);
+          e1 = z1[0]; e2 = z2[0];
+          for (int q = 1; q < 4 && k + q < d; ++q) { eps_s[b * 2 * d + k + q] = z1[q]; eps_s[b * 2 * d + d + k + q] = z2[q]; }
+        }
       }
-      ex_s[i] = v;
+      ex_s[b * E + u + k] = ms; ex_s[b * E + u + d + k] = ls;
+      if (p.eps || (k & 3) == 0 || b >= nb) { eps_s[b * 2 * d + k] = e1; eps_s[b * 2 * d + d + k] = e2; }
     }
-    if (p.eps) {
-      for (int i = ctid; i < TBR * 2 * d; i += TK_NCT) {
-        const int b = i / (2 * d), k = i - b * 2 * d;
-        float v = 0.f;
-        if (b < nb) { const float* e0 = p.eps + ((size_t)t * 2 * p.B + b0 + b) * d; v = (k < d) ? e0[k] : e0[(size_t)p.B * d + k - d]; }
-        eps_s[i] = v;
-      }
-    } else {
-      const int nblk = (d + 3) >> 2;
-      for (int i = ctid; i < TBR * 2 * nblk; i += TK_NCT) {
-        const int b = i / (2 * nblk), r = i - b * 2 * nblk, which = r / nblk, blk = r - which * nblk;
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (b < nb) philox_normal4(p.seed, p.step0 + t, p.trial_offset + b0 + b, which, blk, z);
-        for (int k = 0; k < 4; ++k)
-          if (blk * 4 + k < d) eps_s[b * 2 * d + which * d + blk * 4 + k] = z[k];
-      }
+    #pragma unroll 1
+    for (int i = ctid; i < TBR * u; i += TK_NCT) {
+      const int b = i / u, e = i - b * u;
+      ex_s[b * E + e] = (b < nb) ? p.u_in[(row0 + b) * u + e] : 0.f;
     }
     cb_sync();
     TK_STAMP(p, t, j, 0, 1);
+    #pragma unroll 1
     for (int i = ctid; i < TBR * du; i += TK_NCT) {
       const int b = i / du, k = i - b * du;
       float v;
-      if (k < d) v = ex_s[b * E + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * ex_s[b * E + u + d + k]);
+      if (k < d) v = ex_s[b * E + u + k] + eps_s[b * 2 * d + k] * __expf(0.5f * ex_s[b * E + u + d + k]);
       else v = ex_s[b * E + (k - d)];
       xu_s[i] = v;
     }
@@ -335,42 +455,51 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
     // pad rows are zero
     unsigned char* ph = pg;
     unsigned char* plo = pg + pl.PWC * TBR * 128;
-    for (int b = cw; b < TBR; b += TK_NCW) {
-      for (int r = lane; r < pl.PW; r += 32) {
-        float v = 0.f;
-        if (b < nb && r < R) {
-          float d2 = 0.f;
-          for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[r * du + c]; d2 = fmaf(df, df, d2); }
-          v = expf(d2 * iw_s[r]);
-        }
-        const int o = sw128_off(b, r, TBR);
-        *reinterpret_cast<float*>(ph + o) = v;
-        *reinterpret_cast<float*>(plo + o) = v - tf32_trunc_f(v);
+    #pragma unroll 1
+    for (int i = ctid; i < TBR * pl.PW; i += TK_NCT) {
+      const int b = i / pl.PW, r = i - b * pl.PW;
+      float v = 0.f;
+      if (b < nb && r < R) {
+        float d2 = 0.f;
+        #pragma unroll 1
+        for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[r * du + c]; d2 = fmaf(df, df, d2); }
+        v = __expf(d2 * iw_s[r]);
       }
+      const int o = sw128_off(b, r, TBR);
+      *reinterpret_cast<float*>(ph + o) = v;
+      *reinterpret_cast<float*>(plo + o) = v - tf32_trunc_f(v);
     }
     tk_signal(&bars[BK_CPHI]);
     TK_STAMP(p, t, j, 0, 4);
-    // observations of this tile (TMA) -> append [u | m_s | l_s | 1] behind them (vjf/recognition.py:32-37; the ones column
-    // carries the bias through the MMAs), then the lo image of the whole input tile
+    // observations of this tile (TMA) -> [u | m_s | l_s | 1] appended behind them (vjf/recognition.py:32-37; the ones column
+    // carries the bias through the MMAs) and the lo image of the whole input tile, in one pass over the 16-byte pieces
     tk_wait(&bars[BK_YFULL0 + buf], (it / pl.NBUF) & 1);
     TK_STAMP(p, t, j, 0, 5);
-    if (pl.NCH > pl.NCY) {  // chunks without observation columns are not written by TMA
-      float4* z = reinterpret_cast<float4*>(in_b + pl.NCY * TBR * 128);
-      for (int i = ctid; i < (pl.NCH - pl.NCY) * TBR * 8; i += TK_NCT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cb_sync();
-    }
-    const int EX1 = E + 1;
-    for (int i = ctid; i < TBR * EX1; i += TK_NCT) {
-      const int b = i / EX1, e = i - b * EX1;
-      const float v = (b < nb) ? (e < E ? ex_s[b * E + e] : 1.0f) : 0.f;
-      *reinterpret_cast<float*>(in_b + sw128_off(b, D + e, TBR)) = v;
-    }
-    cb_sync();
     {
-      const float4* src = reinterpret_cast<const float4*>(in_b);
+      float4* img = reinterpret_cast<float4*>(in_b);
       float4* dst = reinterpret_cast<float4*>(inlo_b);
+      const int c_x = D >> 5;  // first chunk that holds appended columns
+      #pragma unroll 1
       for (int i = ctid; i < pl.NCH * TBR * 8; i += TK_NCT) {
-        const float4 x = src[i];
+        const int c = i / (TBR * 8), rr = (i >> 3) % TBR;
+        float4 x;
+        if (c < c_x) {
+          x = img[i];
+        } else {
+          const int col0 = 32 * c + (((i & 7) ^ (rr & 7)) << 2);  // logical columns of this physical piece
+          float v[4];
+          if (c < pl.NCY && col0 + 3 < D) { x = img[i]; v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
+          else {
+            if (c < pl.NCY) { x = img[i]; v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; } else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = col0 + q - D;
+              if (e >= 0) v[q] = (rr < nb) ? (e < E ? ex_s[rr * E + e] : (e == E ? 1.0f : 0.f)) : 0.f;
+            }
+            x = make_float4(v[0], v[1], v[2], v[3]);
+            img[i] = x;
+          }
+        }
         dst[i] = make_float4(x.x - tf32_trunc_f(x.x), x.y - tf32_trunc_f(x.y), x.z - tf32_trunc_f(x.z), x.w - tf32_trunc_f(x.w));
       }
     }
@@ -386,102 +515,76 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
     const int g = cw & 3, si = cw >> 2, nsw = (g == 3) ? 3 : 4;
     if (g * 32 < TBR) {
       const int row = g * 32 + lane;
-      for (int un = si; un < (H >> 3); un += nsw) {
-        float v[8];
-        tmem_ld8(tmem + ((uint32_t)(g * 32) << 16) + pl.c_d1 + 8 * un, v);
+      #pragma unroll 1
+      for (int un = si; un < (H >> 4); un += nsw) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_d1 + 16 * un, v);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) hs[row * ldhs + 8 * un + jj] = tanhf(v[jj]);
+        for (int jj = 0; jj < 16; ++jj) hs[row * ldhs + 16 * un + jj] = tk_tanh(v[jj]);
       }
     }
   }
   tc_fence_before();
   cb_sync();
   TK_STAMP(p, t, j, 0, 8);
-  for (int i = ctid; i < TBR * d; i += TK_NCT) {
-    const int b = i / d, k = i - b * d;
-    float m = 0.f, lv = 0.f, x = 0.f, dxv = 0.f;
-    if (b < nb) {
-      float m1 = 0.f, l1 = 0.f;
+  // heads: eight threads per (trial, state dimension), each over every eighth hidden unit; xor-shuffle reduction
+  #pragma unroll 1
+  for (int i0 = 0; i0 < TBR * d * 8; i0 += TK_NCT) {
+    const int i = i0 + ctid, nq = i & 7, bk = i >> 3;
+    const bool ok = bk < TBR * d;
+    const int b = ok ? bk / d : 0, k = ok ? bk - b * d : 0;
+    float m = 0.f, lv = 0.f;
+    if (ok && b < nb) {
       const float* hr = hs + b * ldhs;
-      int n = 0;
-      for (; n + 1 < H; n += 2) {
-        m = fmaf(hr[n], hm_s[n * d + k], m); lv = fmaf(hr[n], hv_s[n * d + k], lv);
-        m1 = fmaf(hr[n + 1], hm_s[(n + 1) * d + k], m1); l1 = fmaf(hr[n + 1], hv_s[(n + 1) * d + k], l1);
-      }
-      m += m1; lv += l1 + hv_s[H * d + k];
-      x = m + eps_s[b * 2 * d + d + k] * expf(0.5f * lv);
-      dxv = x - xu_s[b * du + k];
-      acc.sc[SC_SDX] = fmaf(dxv, dxv, acc.sc[SC_SDX]);
-      p.mu[((size_t)t * p.B + b0 + b) * d + k] = m;       // posterior of this step (model.py:218-221, :305-307)
-      p.logvar[((size_t)t * p.B + b0 + b) * d + k] = lv;
+      #pragma unroll 1
+      for (int n = nq; n < H; n += 8) { const float h = hr[n]; m = fmaf(h, hm_s[n * d + k], m); lv = fmaf(h, hv_s[n * d + k], lv); }
     }
-    mt_s[i] = m; lt_s[i] = lv; xt_s[i] = x; dx_s[i] = dxv;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { m += __shfl_xor_sync(0xffffffffu, m, o); lv += __shfl_xor_sync(0xffffffffu, lv, o); }
+    if (ok && nq == 0) {
+      float x = 0.f, dxv = 0.f;
+      if (b < nb) {
+        lv += hv_s[H * d + k];
+        x = m + eps_s[b * 2 * d + d + k] * __expf(0.5f * lv);
+        dxv = x - xu_s[b * du + k];
+        acc.sc[SC_SDX] = fmaf(dxv, dxv, acc.sc[SC_SDX]);
+        p.mu[((size_t)t * p.B + b0 + b) * d + k] = m;       // posterior of this step (model.py:218-221, :305-307)
+        p.logvar[((size_t)t * p.B + b0 + b) * d + k] = lv;
+      } else { m = 0.f; lv = 0.f; }
+      mt_s[bk] = m; lt_s[bk] = lv; xt_s[bk] = x; dx_s[bk] = dxv;
+    }
   }
   TK_STAMP(p, t, j, 0, 9);
   // ---- the input tile becomes the MN-major operand of the weight gradient: permute every 128-byte row in place ----
+  #pragma unroll 1
   for (int i = ctid; i < 2 * pl.NCH * TBR; i += TK_NCT) {
     const int im = i / (pl.NCH * TBR), rr = i - im * (pl.NCH * TBR);
     tk_permute_row((im ? inlo_b : in_b) + rr * 128, rr % TBR);
   }
   cb_sync();
-
   TK_STAMP(p, t, j, 0, 10);
-  // ---- LK: decoder eta = D xt + bias (model.py:29-30), likelihood terms, d loss / d eta (times B), decoder gradients, g_xt ----
+
+  // ---- LK: decoder eta = D xt + bias (model.py:29-30), likelihood terms, d loss / d eta (times B), decoder gradients, g_xt.
+  //      A warp owns one 32-column chunk of the observations for a subset of the trials, a lane one column; TK_LK_RB trials are
+  //      in flight together so that the cross-lane sums of g_xt are independent shuffle chains ----
   {
     float lam = 0.f;
     if (p.lik == VJF_LIK_GAUSSIAN) {
       if (t > 0) tk_wait_counter(p.ctrl + 4, (unsigned)t);
       lam = __ldcg(st + p.lay.lik_logvar);
     }
-    const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
+    const float e_nlam = __expf(-lam), p_lam = __expf(-0.5f * lam);
     if (cw < pl.NCY * pl.RS) {
-      const int cy = cw % pl.NCY, rs = cw / pl.NCY;
-      const int jcol = 32 * cy + lane;
-      const bool jok = jcol < D;
-      float w[DX], bj = jok ? dec[d * D + jcol] : 0.f;
-#pragma unroll
-      for (int k = 0; k < DX; ++k) w[k] = (jok && (DX == d || k < d)) ? dec[k * D + jcol] : 0.f;
-      for (int b = rs; b < nb; b += pl.RS) {
-        float xt[DX], eta = bj;
-#pragma unroll
-        for (int k = 0; k < DX; ++k) { xt[k] = (DX == d || k < d) ? xt_s[b * d + k] : 0.f; eta = fmaf(w[k], xt[k], eta); }
-        const float yv = *reinterpret_cast<const float*>(in_b + b32_off(b, jcol, TBR));
-        float g = 0.f;
-        if (jok) {
-          if (p.lik == VJF_LIK_GAUSSIAN) {
-            // gaussian_loss(y, eta, lambda), functional.py:55-75 ; update's mse, likelihood.py:36-37
-            const float r = yv - eta;
-            const float rsd = yv * p_lam - eta * p_lam;
-            const float mse = rsd * rsd;
-            if (!isfinite(mse)) acc.sc[SC_BADMSE] += 1.f;
-            acc.sc[SC_RECON] += 0.5f * (mse + lam);
-            acc.sc[SC_SSE] = fmaf(r, r, acc.sc[SC_SSE]);
-            g = -r * e_nlam;
-            acc.sc[6] += r_on ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
-          } else {
-            // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62
-            const float ec = fminf(eta, 10.0f);
-            const float ex = expf(ec);
-            acc.sc[SC_RECON] += ex - yv * ec;
-            g = (eta <= 10.0f) ? (ex - yv) : 0.f;
-            if (eta != eta) { acc.sc[SC_RECON] = eta; g = eta; }  // NaN propagates like torch.clamp
-          }
-          g = r_on ? g : 0.f;
-        }
-        acc.gdb += g;
-#pragma unroll
-        for (int k = 0; k < DX; ++k) {
-          acc.gdw[k] = fmaf(g, xt[k], acc.gdw[k]);
-          const float s = warp_sum(g * w[k]);
-          if (lane == 0 && (DX == d || k < d)) gxp_s[(cy * TBR + b) * d + k] = s;
-        }
-      }
+      if (p.lik == VJF_LIK_GAUSSIAN) tk_lk_rows<DX, VJF_LIK_GAUSSIAN>(p, acc, in_b, xt_s, gxp_s, dec, cw % pl.NCY, cw / pl.NCY, nb, r_on, lam, e_nlam, p_lam);
+      else tk_lk_rows<DX, VJF_LIK_POISSON>(p, acc, in_b, xt_s, gxp_s, dec, cw % pl.NCY, cw / pl.NCY, nb, r_on, lam, e_nlam, p_lam);
     }
     cb_sync();
+    #pragma unroll 1
     for (int i = ctid; i < TBR * d; i += TK_NCT) {
       const int b = i / d, k = i - b * d;
       float s = 0.f;
       if (b < nb)
+        #pragma unroll 1
         for (int cy = 0; cy < pl.NCY; ++cy) s += gxp_s[(cy * TBR + b) * d + k];
       gxt_s[i] = s;
     }
@@ -493,11 +596,34 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
   tk_wait(&bars[BK_FL], par);
   tc_fence_after();
   TK_STAMP(p, t, j, 0, 12);
+  #pragma unroll 1
   for (int i = ctid; i < 2 * pl.PWC * TBR; i += TK_NCT) tk_permute_row(pg + i * 128, i % TBR);
+  // FL = phi [w_chol | w_mean] from tensor memory: p_logvar = log |phi w_chol|^2, p_mean = xs + phi W (module.py:75-77,
+  // model.py:338); the warps of a lane group share its columns, the partial sums of squares meet in gxp_s
+  {
+    const int g = cw & 3, si = cw >> 2, nsw = (g == 3) ? 3 : 4;
+    if (g * 32 < TBR) {
+      const int row = g * 32 + lane;
+      float q = 0.f;
+      #pragma unroll 1
+      for (int un = si; un < (pl.NQ >> 4); un += nsw) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_fl + 16 * un, v);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int col = 16 * un + jj;
+          if (col < pl.Rk) q = fmaf(v[jj], v[jj], q);
+          else if (col < pl.Rk + d) pm_s[row * d + col - pl.Rk] = xu_s[row * du + col - pl.Rk] + v[jj];
+        }
+      }
+      gxp_s[pl.NCY * TBR * d + si * TBR + row] = q;
+    }
+  }
   cb_sync();
   {
     unsigned char* ph = pg;
     unsigned char* plo = pg + pl.PWC * TBR * 128;
+    #pragma unroll 1
     for (int i = ctid; i < TBR * d; i += TK_NCT) {
       const int b = i / d, k = i - b * d;
       const float v = dx_s[i];
@@ -505,31 +631,13 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
       *reinterpret_cast<float*>(ph + o) = v;
       *reinterpret_cast<float*>(plo + o) = v - tf32_trunc_f(v);
     }
-  }
-  // FL = phi [w_chol | w_mean] from tensor memory: p_logvar = log |phi w_chol|^2, p_mean = xs + phi W (module.py:75-77, model.py:338)
-  if (cw * 32 < TBR) {
-    const int row = cw * 32 + lane;
-    float q = 0.f, pmv[DX];
-#pragma unroll
-    for (int k = 0; k < DX; ++k) pmv[k] = 0.f;
-    for (int un = 0; un < (pl.NQ >> 3); ++un) {
-      float v[8];
-      tmem_ld8(tmem + ((uint32_t)(cw * 32) << 16) + pl.c_fl + 8 * un, v);
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int col = 8 * un + jj;
-        if (col < pl.Rk) q = fmaf(v[jj], v[jj], q);
-        else {
-#pragma unroll
-          for (int k = 0; k < DX; ++k)
-            if (col - pl.Rk == k) pmv[k] = v[jj];
-        }
-      }
+    if (ctid < TBR) {
+      const int g = ctid >> 5, nsw = (g == 3) ? 3 : 4;
+      float q = 0.f;
+      #pragma unroll 1
+      for (int si = 0; si < nsw && si < (pl.NQ >> 4); ++si) q += gxp_s[pl.NCY * TBR * d + si * TBR + ctid];
+      plv_s[ctid] = __logf(q);
     }
-    plv_s[row] = logf(q);
-#pragma unroll
-    for (int k = 0; k < DX; ++k)
-      if (DX == d || k < d) pm_s[row * d + k] = xu_s[row * du + k] + pmv[k];
   }
   tk_signal(&bars[BK_CPHIT]);
   TK_STAMP(p, t, j, 0, 13);
@@ -539,8 +647,9 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
   TK_STAMP(p, t, j, 0, 14);
   {
     const float gam = __ldcg(st + p.lay.tr_logvar);
-    const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
+    const float e_ngam = __expf(-gam), p_gam = __expf(-0.5f * gam);
     // dynamics NLL (functional.py:55-75 via model.py:390-391), entropy (functional.py:25-29), g_mt and g_lt (times B)
+    #pragma unroll 1
     for (int i = ctid; i < TBR * d; i += TK_NCT) {
       const int b = i / d, k = i - b * d;
       float gm = 0.f, gl = 0.f;
@@ -550,10 +659,10 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
         const float df = pm * p_gam - m * p_gam;
         const float mse = df * df;
         if (!isfinite(mse)) acc.sc[SC_BADMSE] += 1.f;
-        const float tr = expf(plv + lv - gam);
+        const float tr = __expf(plv + lv - gam);
         acc.sc[SC_DYN] += 0.5f * (mse + gam) + 0.5f * tr;
         acc.sc[SC_ENT] += 0.5f * lv;
-        gm = gx; gl = 0.5f * gx * e2 * expf(0.5f * lv);
+        gm = gx; gl = 0.5f * gx * e2 * __expf(0.5f * lv);
         if (h_on) gl -= 0.5f;
         if (d_on) { gm += (m - pm) * e_ngam; gl += 0.5f * tr; }
       }
@@ -578,6 +687,7 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
         wm[hc][k] = ok ? hm_s[(32 * hc + lane) * d + k] : 0.f;
         wv[hc][k] = ok ? hv_s[(32 * hc + lane) * d + k] : 0.f;
       }
+    #pragma unroll 1
     for (int b = cw; b < TBR; b += TK_NCW) {
       float gm[DX], gv[DX];
 #pragma unroll
@@ -603,6 +713,7 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
     }
     if (ctid < d) {
       float s = 0.f;
+      #pragma unroll 1
       for (int b = 0; b < nb; ++b) s += glt_s[b * d + ctid];
       acc.ghvb += s;
     }
@@ -621,6 +732,7 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
   float* sf = reinterpret_cast<float*>(sb + pl.o_f);
   float* scr = reinterpret_cast<float*>(sb + pl.o_pg);  // scratch: the phi / g_pre region + weight ring (dead between steps)
   if (!have_tiles) {
+    #pragma unroll 1
     for (int i = tid; i < p.PS; i += VJF_NT) slot[i] = 0.f;
     return;
   }
@@ -628,27 +740,30 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
   // ---- tensor-memory accumulators: A = phi^T phi, b = phi^T dx ; dW1 (+ bias row) ----
   {
     const int g = warp & 3, si = warp >> 2, row = g * 32 + lane;
-    for (int un = si; un < (pl.NQ >> 3); un += 4) {
-      float v[8];
-      tmem_ld8(tmem + ((uint32_t)(g * 32) << 16) + pl.c_gram + 8 * un, v);
+    #pragma unroll 1
+    for (int un = si; un < (pl.NQ >> 4); un += 4) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_gram + 16 * un, v);
       if (row < R) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int col = 8 * un + jj;
+        for (int jj = 0; jj < 16; ++jj) {
+          const int col = 16 * un + jj;
           if (col < R) slot[p.pa + row * R + col] = v[jj];
           else if (col >= pl.Rk && col < pl.Rk + d) slot[p.pb + row * d + (col - pl.Rk)] = v[jj];
         }
       }
     }
+    #pragma unroll 1
     for (int mb = 0; mb < pl.NBLK; ++mb) {
       const int k1 = 128 * mb + row;
-      for (int un = si; un < (H >> 3); un += 4) {
-        float v[8];
-        tmem_ld8(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dw + mb * H + 8 * un, v);
-        float* o = (k1 < p.K1) ? slot + p.lay.mlp_w[0] + (size_t)k1 * H + 8 * un : ((k1 == p.K1) ? slot + p.lay.mlp_b[0] + 8 * un : nullptr);
+      #pragma unroll 1
+      for (int un = si; un < (H >> 4); un += 4) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dw + mb * H + 16 * un, v);
+        float* o = (k1 < p.K1) ? slot + p.lay.mlp_w[0] + (size_t)k1 * H + 16 * un : ((k1 == p.K1) ? slot + p.lay.mlp_b[0] + 16 * un : nullptr);
         if (o) {
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
     }
@@ -681,22 +796,27 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
   }
   if (tid < d) scrs[16 * VJF_NSCAL + tid] = acc.ghvb;
   __syncthreads();
+  #pragma unroll 1
   for (int i = tid; i < (d + 1) * D; i += VJF_NT) {
     const int k = i / D, j = i - k * D, cy = j >> 5, l = j & 31;
     float s = 0.f;
+    #pragma unroll 1
     for (int rs = 0; rs < pl.RS; ++rs) s += scr[(rs * pl.NCY + cy) * (DX + 1) * 32 + (k < d ? k : DX) * 32 + l];
     if (k < d) slot[p.lay.dec_w + k * D + j] = s;
     else slot[p.lay.dec_b + j] = s;
   }
+  #pragma unroll 1
   for (int i = tid; i < 2 * H * d; i += VJF_NT) {
     const int which = i / (H * d), r = i - which * H * d, n = r / d, k = r - n * d, hc = n >> 5, l = n & 31;
     float s = 0.f;
+    #pragma unroll 1
     for (int w = 0; w < TK_NCW; ++w) s += scrh[w * hstride + ((which * HC + hc) * DX + k) * 32 + l];
     slot[(which ? p.lay.head_v_w : p.lay.head_m_w) + r] = s;
   }
   if (tid < d) slot[p.lay.head_v_b + tid] = scrs[16 * VJF_NSCAL + tid];
   if (tid < VJF_NSCAL) {
     float s = 0.f;
+    #pragma unroll 1
     for (int w = 0; w < TK_NCW; ++w) s += scrs[w * VJF_NSCAL + tid];
     if (tid == 6) slot[p.lay.lik_logvar] = s;  // Gaussian d loss / d lambda (times B)
     else slot[p.ps + tid] = s;
