@@ -33,6 +33,8 @@ struct TilePlan {
   int K1b, NCH, NCY;         // K1 + 1 (ones column = bias), 32-column chunks of the input image, chunks with observation columns
   int Rk, NQ, PW, PWC;       // K of the quadratic form (roundup(R, 8)), N of QUAD / GRAM, phi image width (columns, chunks)
   int HC, NBLK;              // H / 32, 128-row blocks of the layer-1 weight-gradient accumulator
+  int CL0, NBLKLO, c_dwlo;   // first chunk of the input image with a lo image (0 unless the observations are exact in tf32), blocks and
+                             // tensor-memory column of the lo part of the weight gradient
   int NS, SS;                // weight ring: stages, bytes per stage
   int ukimg;                 // bytes of one image (hi or lo) of the [w_chol^T ; w_mean^T] operand
   int RS;                    // row splits of the likelihood stage (warps per observation chunk)

@@ -11,6 +11,6 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_phase_b_kernel(const __grid_con
 #include <cuda.h>
 __global__ void __launch_bounds__(VJF_NT, 1) vjf_tile_kernel(const __grid_constant__ StepParams p, const __grid_constant__ CUtensorMap ymap);
 // host: plan the tile pipeline for a launch (returns 1 when it applies and fills p.tp / the tensor map), launch it
-int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map);
+int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map, cudaStream_t stream);
 int vjf_tile_launch(vjf_handle* h, StepParams& p, const CUtensorMap& map, cudaStream_t s);
 int vjf_tile_create(vjf_handle* h);

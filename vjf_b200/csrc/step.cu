@@ -326,7 +326,7 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
 // the throughput tile pipeline when the shapes are in its plan, else the persistent kernel of k_persistent.cu
 static int launch_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s) {
   CUtensorMap map;
-  const int use_tile = vjf_tile_plan(h, p, p.y, p.y_dtype, T, B, &map);
+  const int use_tile = vjf_tile_plan(h, p, p.y, p.y_dtype, T, B, &map, s);
   if (use_tile < 0) return -2;
   g_vjf_last_kind = use_tile ? 1 : 0;
   if (use_tile) return vjf_tile_launch(h, p, map, s);

@@ -25,6 +25,33 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Are all observations exactly representable in tf32 (integers below 2048, i.e. spike counts)?  Then the tensor core's
+// truncation of the input image loses nothing, the image needs no "lo" companion except for the appended columns, and the
+// tiles can be twice as large.  One pass over the buffer at copy speed; the flag is read back (stream synchronisation).
+__global__ void vjf_y_exact_kernel(const float4* __restrict__ y, size_t n4, const float* __restrict__ tail, int ntail, unsigned* flag) {
+  unsigned bad = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = y[i];
+    bad |= (__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w)) & 0x1fffu;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) bad |= __float_as_uint(tail[threadIdx.x]) & 0x1fffu;
+  if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+static int observations_exact(vjf_handle* h, const void* y, size_t n, cudaStream_t s, bool* exact) {
+  unsigned* flag = h->sync_words + 48;
+  VJF_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(unsigned), s));
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((size_t)h->num_sms * 8, std::max<size_t>(1, (n4 + 255) / 256));
+  vjf_y_exact_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(y), n4, reinterpret_cast<const float*>(y) + n4 * 4, (int)(n - n4 * 4), flag);
+  ++g_vjf_launches;
+  unsigned host = 1;
+  VJF_CUDA_OK(cudaMemcpyAsync(&host, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  VJF_CUDA_OK(cudaStreamSynchronize(s));
+  *exact = host == 0;
+  return 0;
+}
+
 // dimensions that do not depend on the batch
 static bool tile_static_dims(const StepParams& p, TilePlan& pl) {
   const int H = p.H[0];
@@ -42,7 +69,8 @@ static bool tile_static_dims(const StepParams& p, TilePlan& pl) {
   pl.SS = 2 * H * 128;
   if (pl.PWC > 4 || pl.NQ > 256 || pl.NCY > TK_NCW) return false;
   pl.c_d1 = 0; pl.c_fl = H; pl.c_gram = H + pl.NQ; pl.c_dw = H + 2 * pl.NQ;
-  if (pl.c_dw + pl.NBLK * H > 512) return false;
+  pl.c_dwlo = pl.c_dw + pl.NBLK * H;
+  if (pl.c_dwlo + pl.NBLK * H > 512) return false;  // (general observations: a lo block for every block)
   return true;
 }
 
@@ -63,7 +91,7 @@ int vjf_tile_create(vjf_handle* h) {
 
 // Returns 1 when the tile pipeline runs this launch (p.tp and the tensor map are filled), 0 when the launch stays on the
 // persistent kernel of k_persistent.cu (shapes outside the plan), < 0 on error.
-int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map) {
+int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map, cudaStream_t stream) {
   static const bool disabled = getenv("VJF_B200_NO_TILE") != nullptr;
   p.tp.on = 0;
   if (disabled || !h->w1k || y_dtype != VJF_Y_F32 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 || h->num_sms < 2 || !encode_fn()) return 0;
@@ -72,21 +100,31 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   if (!tile_static_dims(p, pl)) return 0;
   const int H = p.H[0], d = p.d, D = p.D;
   static const int force_tbr = getenv("VJF_B200_TILE_ROWS") ? atoi(getenv("VJF_B200_TILE_ROWS")) : 0;
-  pl.TBR = force_tbr ? force_tbr : 32;
+  static const bool no_exact = getenv("VJF_B200_NO_EXACT") != nullptr;
+  // spike counts (Poisson likelihood): are they exact in tf32?
+  bool exact = false;
+  if (p.lik == VJF_LIK_POISSON && !no_exact && observations_exact(h, y, (size_t)T * B * D, stream, &exact)) return -1;
+  pl.CL0 = exact ? D / 32 : 0;
+  pl.NBLKLO = pl.NBLK - pl.CL0 / 4;  // lo accumulator blocks, aligned with the blocks CL0 / 4 .. of the hi part
+  // tiles of 32 trials; 64 when the lo image is small (exact observations) and every trial CTA gets more than one tile
+  pl.TBR = force_tbr ? force_tbr : ((exact && (B + 31) / 32 > h->max_slots - 1) ? 64 : 32);
   // one tile per trial CTA (latency regime): the second observation buffer would never be used -- its space goes to the
   // weight ring instead (deeper prefetch of the layer-1 weight chunks)
   const int ntiles = (B + pl.TBR - 1) / pl.TBR;
-  pl.NBUF = (ntiles <= h->max_slots - 1) ? 1 : 2;
+  const int nbuf_pref = (ntiles <= h->max_slots - 1) ? 1 : 2;
   pl.RS = std::max(1, std::min(TK_NCW / pl.NCY, pl.TBR));
   const int TBR = pl.TBR, chunkB = TBR * 128;
   static const int force_ns = getenv("VJF_B200_TILE_NS") ? atoi(getenv("VJF_B200_TILE_NS")) : 0;
   const int ns_hi = force_ns ? force_ns : std::min(TK_MAXNS, pl.NCH);
-  for (pl.NS = ns_hi; pl.NS >= 2; --pl.NS) {
+  bool fits = false;
+  for (int nbuf = nbuf_pref; nbuf >= 1 && !fits; --nbuf)
+  for (int ns = ns_hi; ns >= (nbuf == 2 ? 3 : 2) && !fits; --ns) {
+  pl.NBUF = nbuf; pl.NS = ns;
   int o = 0;
   pl.o_in[0] = o; o += pl.NCH * chunkB;
   pl.o_in[1] = o; o += (pl.NBUF > 1 ? pl.NCH * chunkB : 0);
   if (pl.NBUF == 1) pl.o_in[1] = pl.o_in[0];
-  pl.o_inlo = o; o += pl.NCH * chunkB;
+  pl.o_inlo = o; o += (pl.NCH - pl.CL0) * chunkB;
   pl.o_pg = o; o += std::max(2 * pl.PWC, 2 * pl.HC) * chunkB;
   pl.o_ring = o; o += pl.NS * pl.SS;
   pl.o_uk = o; o += 2 * pl.ukimg;
@@ -112,9 +150,9 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   pl.f_bar = take(2 * 32);  // mbarriers (8 bytes each; the float area starts 16-byte aligned)
   pl.f_total = f;
   pl.smem_bytes = pl.o_f + f * 4 + 1024;  // + slack for the 1024-byte alignment of the base
-  if ((size_t)pl.smem_bytes <= h->smem_limit) break;
+  if ((size_t)pl.smem_bytes <= h->smem_limit) { fits = true; break; }
   }
-  if (pl.NS < 2) return 0;
+  if (!fits) return 0;
   // scratch of the per-step flush (register accumulators of 15 warps) and workspace of the shared phases B1 / B2
   const int DX = d <= 2 ? 2 : (d == 3 ? 3 : (d == 4 ? 4 : 8));
   const int flush_floats = TK_NCW * (DX + 1) * 32 + TK_NCW * 2 * pl.HC * DX * 32 + 16 * VJF_NSCAL + 16 + 16;

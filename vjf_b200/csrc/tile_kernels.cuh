@@ -196,13 +196,14 @@ static __device__ void tk_control_step(const StepParams& p, const CUtensorMap* y
       const uint32_t s = u.rc % pl.NS;
       tku_wait(u.bbase + 8 * (BK_WFULL0 + s), (u.rc / pl.NS) & 1);
       tc_fence_after();
-      const uint64_t a_hi = tk_kmaj(u.sbase + pl.o_in[buf] + c * chunkB), a_lo = tk_kmaj(u.sbase + pl.o_inlo + c * chunkB);
+      // (lo image: only the chunks from CL0 on exist -- all of them unless the observations are exact in tf32)
+      const uint64_t a_hi = tk_kmaj(u.sbase + pl.o_in[buf] + c * chunkB), a_lo = tk_kmaj(u.sbase + pl.o_inlo + (c - pl.CL0) * chunkB);
       const uint64_t b_hi = tk_kmaj(u.sbase + pl.o_ring + s * pl.SS), b_lo = tk_kmaj(u.sbase + pl.o_ring + s * pl.SS + H * 128);
       const int nks = min(4, (pl.K1b - 32 * c + 7) >> 3);
       #pragma unroll 1
       for (int ks = 0; ks < nks; ++ks) {  // a k-step advances 32 bytes inside the 128-byte rows: +2 in the descriptor's address field
-        tku_mma(u.tmem + pl.c_d1, a_lo + 2 * ks, b_hi + 2 * ks, id_fwd, (c | ks) ? 1u : 0u);
-        tku_mma(u.tmem + pl.c_d1, a_hi + 2 * ks, b_lo + 2 * ks, id_fwd, 1u);
+        tku_mma(u.tmem + pl.c_d1, a_hi + 2 * ks, b_lo + 2 * ks, id_fwd, (c | ks) ? 1u : 0u);
+        if (c >= pl.CL0) tku_mma(u.tmem + pl.c_d1, a_lo + 2 * ks, b_hi + 2 * ks, id_fwd, 1u);
         tku_mma(u.tmem + pl.c_d1, a_hi + 2 * ks, b_hi + 2 * ks, id_fwd, 1u);
       }
       tku_commit(u.bbase + 8 * (BK_WEMPTY0 + s));
@@ -267,14 +268,23 @@ static __device__ void tk_control_step(const StepParams& p, const CUtensorMap* y
       const uint64_t bh = tk_mnmaj(u.sbase + pl.o_pg, chunkB), bl = tk_mnmaj(u.sbase + pl.o_pg + pl.HC * chunkB, chunkB);
       #pragma unroll 1
       for (int mb = 0; mb < pl.NBLK; ++mb) {
-        const uint64_t ah = tk_mnmaj(u.sbase + pl.o_in[buf] + 4 * mb * chunkB, chunkB), al = tk_mnmaj(u.sbase + pl.o_inlo + 4 * mb * chunkB, chunkB);
+        const uint64_t ah = tk_mnmaj(u.sbase + pl.o_in[buf] + 4 * mb * chunkB, chunkB);
         const uint32_t d = u.tmem + pl.c_dw + mb * H;
-        #pragma unroll 1
+#pragma unroll 1
         for (int ks = 0; ks < (TBR >> 3); ++ks) {
-          tku_mma(d, al + 64 * ks, bh + 64 * ks, id_dw, (j | ks) ? 1u : 0u);
-          tku_mma(d, ah + 64 * ks, bl + 64 * ks, id_dw, 1u);
+          tku_mma(d, ah + 64 * ks, bl + 64 * ks, id_dw, (j | ks) ? 1u : 0u);
           tku_mma(d, ah + 64 * ks, bh + 64 * ks, id_dw, 1u);
         }
+      }
+      // lo part of the input image (chunks CL0 ..): its own accumulator blocks, aligned with the blocks CL0 / 4 .. of the hi part
+      // (the descriptor may start before the lo image; rows of chunks without a lo image multiply whatever lies there and
+      // are never read back)
+#pragma unroll 1
+      for (int mb = 0; mb < pl.NBLKLO; ++mb) {
+        const uint64_t al = tk_mnmaj(u.sbase + pl.o_inlo + (4 * ((pl.CL0 >> 2) + mb) - pl.CL0) * chunkB, chunkB);
+        const uint32_t d = u.tmem + pl.c_dwlo + mb * H;
+#pragma unroll 1
+        for (int ks = 0; ks < (TBR >> 3); ++ks) tku_mma(d, al + 64 * ks, bh + 64 * ks, id_dw, (j | ks) ? 1u : 0u);
       }
       tku_commit(u.bbase + 8 * BK_DW);
       TK_STAMP(p, t, j, TK_CTRL * 32, 41);
@@ -479,8 +489,9 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
       float4* img = reinterpret_cast<float4*>(in_b);
       float4* dst = reinterpret_cast<float4*>(inlo_b);
       const int c_x = D >> 5;  // first chunk that holds appended columns
-      #pragma unroll 1
-      for (int i = ctid; i < pl.NCH * TBR * 8; i += TK_NCT) {
+      // exact observations (CL0 = c_x): the chunks before c_x need neither the appended columns nor a lo image
+#pragma unroll 1
+      for (int i = pl.CL0 * TBR * 8 + ctid; i < pl.NCH * TBR * 8; i += TK_NCT) {
         const int c = i / (TBR * 8), rr = (i >> 3) % TBR;
         float4 x;
         if (c < c_x) {
@@ -500,7 +511,7 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
             img[i] = x;
           }
         }
-        dst[i] = make_float4(x.x - tf32_trunc_f(x.x), x.y - tf32_trunc_f(x.y), x.z - tf32_trunc_f(x.z), x.w - tf32_trunc_f(x.w));
+        dst[i - pl.CL0 * TBR * 8] = make_float4(x.x - tf32_trunc_f(x.x), x.y - tf32_trunc_f(x.y), x.z - tf32_trunc_f(x.z), x.w - tf32_trunc_f(x.w));
       }
     }
     tk_signal(&bars[BK_CX]);
@@ -557,8 +568,8 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
   TK_STAMP(p, t, j, 0, 9);
   // ---- the input tile becomes the MN-major operand of the weight gradient: permute every 128-byte row in place ----
   #pragma unroll 1
-  for (int i = ctid; i < 2 * pl.NCH * TBR; i += TK_NCT) {
-    const int im = i / (pl.NCH * TBR), rr = i - im * (pl.NCH * TBR);
+  for (int i = ctid; i < (2 * pl.NCH - pl.CL0) * TBR; i += TK_NCT) {
+    const int im = i >= pl.NCH * TBR, rr = i - im * (pl.NCH * TBR);
     tk_permute_row((im ? inlo_b : in_b) + rr * 128, rr % TBR);
   }
   cb_sync();
@@ -760,6 +771,14 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
       for (int un = si; un < (H >> 4); un += 4) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dw + mb * H + 16 * un, v);
+        if (mb >= (pl.CL0 >> 2)) {  // + the lo part of the input image (same rows of its own accumulator block)
+          float vl[16];
+          tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dwlo + (mb - (pl.CL0 >> 2)) * H + 16 * un, vl);
+          if (k1 >= 32 * pl.CL0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] += vl[q];
+          }
+        }
         float* o = (k1 < p.K1) ? slot + p.lay.mlp_w[0] + (size_t)k1 * H + 16 * un : ((k1 == p.K1) ? slot + p.lay.mlp_b[0] + 16 * un : nullptr);
         if (o) {
 #pragma unroll
