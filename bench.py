@@ -32,6 +32,11 @@ sys.path.insert(0, ROOT)
 
 C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[64], likelihood="poisson",
           trials_per_gpu=4096, T=256)
+# BASELINE.json configs[3]: neural-population scale, 65536 trials sharded over the GPUs (strong scaling), SURVEY.md 8d row C4
+C4 = dict(name="C4-population-poisson", ydim=2000, xdim=8, udim=0, n_rbf=64, hidden=[128], likelihood="poisson",
+          global_trials=65536, T=8)
+# the same C2 model in the throughput regime: enough trials per step that the serial part of a step is amortised
+C2_THROUGHPUT = dict(trials_per_gpu=65536, T=16)
 DATA_DESC = "synthetic (Lorenz-driven Poisson counts, random-init parameters; CPU-seeded, identical for both arms)"
 ALGO_BYTES_PER_TRIAL_STEP = lambda c, y_bytes=4: y_bytes * c["ydim"] + 4 * (c["udim"] + 4 * c["xdim"])
 
@@ -134,14 +139,17 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def measured_traffic_per_time_step():
-    """DRAM bytes per time step of the persistent kernel from the committed ncu --set full capture (C2 shapes)."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    try:
-        t = json.load(open(p))
-        return float(t["dram_bytes_read_per_time_step"]) + float(t["dram_bytes_write_per_time_step"])
-    except Exception:
-        return None
+def measured_traffic_per_time_step(kernel):
+    """DRAM bytes per time step of the time-loop kernel from the committed ncu --set full capture (C2 shapes, 4096 trials):
+    profiles/traffic_r02.json for the tile pipeline, traffic_r01.json for the persistent kernel."""
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if t.get("kernel", "vjf_persistent_kernel") == kernel:
+                return float(t["dram_bytes_read_per_time_step"]) + float(t["dram_bytes_write_per_time_step"]), "profiles/" + name
+        except Exception:
+            pass
+    return None, None
 
 
 def measured_peak_gbs():
@@ -237,11 +245,13 @@ class ReferenceRunner:
             self.tape.load(self.eps[t])
             q, loss = m.filter(self.y[t], None, q, sgd=True, update=True, warm_up=False)
         dt = time.perf_counter() - t0
-        self.last_loss = float(loss)
+        self.last_loss = float(loss.detach())
         return dt
 
     def describe(self, dt):
-        return (f"first {self.T_s} of the {self.cfg['T']} time steps x {self.B} trials ({dt:.1f} s), UNMODIFIED reference "
+        span = (f"first {self.T_s} of the {self.cfg['T']} time steps" if self.T_s <= self.cfg["T"] else
+                f"{self.T_s} time steps (the {self.cfg['T']}-step workload continued with the same generator)")
+        return (f"{span} x {self.B} trials ({dt:.1f} s), UNMODIFIED reference "
                 f"vjf.model.VJF.filter (oracle/_ref), fp32, torch {self._tv()} with {os.cpu_count()} threads on {cpu_model()}; "
                 f"same observations and initial parameters as the GPU arm, N(0,1) noise from a seeded tape")
 
@@ -311,6 +321,92 @@ def workload_config(cfg, n_gpus):
                          (cfg["trials_per_gpu"] * cfg["T"] * cfg["ydim"] * 4 / 1e6)}
 
 
+
+def synthetic_counts_gpu(T, B, D, d, dev, seed):
+    """Poisson counts driven by a smooth d-dimensional latent (coupled oscillators), generated on the device: used where the
+    CPU Lorenz recipe would take minutes (65536 trials, ydim 2000)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    t = torch.arange(T, device=dev, dtype=torch.float32)[:, None, None] * 0.05
+    ph = torch.rand(1, B, d, device=dev, generator=g) * 6.283185
+    x = torch.sin(t * (1 + torch.arange(d, device=dev, dtype=torch.float32)) + ph)
+    Cm = torch.randn(d, D, device=dev, generator=g) / d ** 0.5
+    return torch.poisson(torch.exp(torch.clamp(x @ Cm - 1.0, max=3.0)), generator=g)
+
+
+def time_runs(fn, reps):
+    """Mean CUDA-event time (ms) of fn() over reps calls, after one warm-up call."""
+    import torch
+    fn(); torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+
+def tensor_flops_per_trial_step(cfg):
+    """Tensor-core FLOPs the tile pipeline issues per trial-step (the C2 path is tensor-bound before it is
+    HBM-bound once fp32-grade accuracy is bought with hi/lo operand pairs): layer-1 forward and weight gradient over
+    K1 + 1 columns, quadratic form and Gram matrix over the padded RBF width; two products per contraction on exact count
+    columns, three elsewhere (counted as three: an upper bound of the work, a lower bound of the implied peak time)."""
+    D, d, R, H = cfg["ydim"], cfg["xdim"], cfg["n_rbf"], cfg["hidden"][0]
+    K1 = D + cfg["udim"] + 2 * d + 1
+    Rk = (R + 7) // 8 * 8
+    NQ = (Rk + d + 15) // 16 * 16
+    return 3 * 2 * (2 * K1 * H + Rk * NQ + NQ * NQ)
+
+
+def sharded_parity_check(dev, world, rank, seed=5):
+    """Short sharded run (C2 shapes, 192 trials per rank, 4 steps, noise tape) against the fp64 oracle of the WHOLE batch on
+    rank 0, and bitwise identity of the replicas: SCALE lines carry the evidence that the multi-GPU path computes the same
+    thing (the driver's GPU tests run on one GPU only)."""
+    import torch
+    import torch.distributed as dist
+    from vjf_b200.model import VJF
+    from vjf_b200.distributed import ShardedVJF
+    cfg, Bl, T = C2, 192, 4
+    D, d = cfg["ydim"], cfg["xdim"]
+    Bg = Bl * world
+    rng = np.random.default_rng(seed)
+    t = np.arange(T)[:, None, None] * 0.05
+    ph = rng.uniform(0, 2 * np.pi, (1, Bg, d))
+    Cm = rng.normal(size=(d, D)) / np.sqrt(d)
+    y = rng.poisson(np.exp(np.clip(np.sin(t * (1 + np.arange(d)) + ph) @ Cm - 1.0, None, 3.0))).astype(np.float32)
+    eps = rng.normal(size=(T, 2, Bg, d)).astype(np.float32)
+    torch.manual_seed(seed)
+    m = VJF.make_model(D, d, 0, cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], lr=1e-3, max_trials=Bl, seed=3, device=dev)
+    m.load_full_state(bench_state(cfg, seed=4321))
+    st0 = {k: v.detach().cpu().numpy() for k, v in m.full_state().items()}
+    runner = ShardedVJF(m).connect()
+    lo = rank * Bl
+    mu, lv, losses = runner.run(torch.as_tensor(y[:, lo:lo + Bl]).to(dev), eps=torch.as_tensor(np.ascontiguousarray(eps[:, :, lo:lo + Bl])).to(dev))
+    torch.cuda.synchronize()
+    status = m.status()
+    flat = m._flat.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    mus = [torch.empty_like(mu) for _ in range(world)]
+    dist.all_gather(mus, mu.contiguous())
+    out = {"trials_per_rank": Bl, "time_steps": T, "replicas_identical": bool(same.item()), "status_word": int(status)}
+    if rank == 0:
+        from oracle.vjf_oracle import OracleVJF
+        o = OracleVJF(D, d, 0, cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], lr=1e-3, dtype=np.float64)
+        o.set_state(st0)
+        omu, olv, ol = o.run(y.astype(np.float64), None, eps=eps.astype(np.float64))
+        got = torch.cat(mus, 1).cpu().numpy()
+        want = o.get_state()
+        have = {k: v.detach().cpu().numpy() for k, v in m.full_state().items()}
+        perr = max(float(np.abs(np.asarray(have[k], np.float64) - want[k]).max() / max(1.0, np.abs(want[k]).max()))
+                   for k in want if k in have and k not in ("w_chol", "w_pchol"))
+        out.update({"max_err_mu": float(np.abs(got - omu).max()), "max_rel_err_losses": float(np.abs(losses.cpu().numpy() - ol).max() / max(1.0, np.abs(ol).max())),
+                    "max_rel_err_parameters": perr, "against": "fp64 oracle of the whole batch (oracle/vjf_oracle.py)"})
+    del runner, m
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, cfg):
     import ctypes as C
@@ -329,6 +425,7 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     B, T, D, d = cfg["trials_per_gpu"], cfg["T"], cfg["ydim"], cfg["xdim"]
     lib = _lib.load()
+    parity = sharded_parity_check(dev, world, rank) if world > 1 else None
 
     torch.manual_seed(1234)
     model = VJF.make_model(D, d, cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], max_trials=B, seed=99, device=dev)
@@ -353,7 +450,7 @@ def run_ours(args, cfg):
 
         def step_e2e():
             model._flat.copy_(state0)
-            runner.run_host(y_host, mu_h, lv_h, ls_h)
+            runner.run_host(y_host, mu_h, lv_h, ls_h, chunk_steps=args.chunk)
     else:
         def step_dev():
             model._flat.copy_(state0)
@@ -400,6 +497,7 @@ def run_ours(args, cfg):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     clocks = sampler.stop()
     status = model.status()
+    kind = int(lib.vjf_last_launch_kind())
 
     # ---- timed region: end to end through the C ABI with pinned host buffers ----
     step_e2e()
@@ -434,6 +532,87 @@ def run_ours(args, cfg):
                       "d2h_bytes_per_step": int((mu_h.numel() + lv_h.numel() + ls_h.numel()) * 4),
                       "api": "vjf_run_host with y_dtype = VJF_Y_U8 (counts as bytes)", "status_word": int(model.status())}
 
+
+    # ---- further regimes (reported beside the headline; same kernels, CUDA-event timed, device-resident inputs) ----
+    extras = {}
+    peak, peak_src = measured_peak_gbs()
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tf32_peak = float(peaks["bf16_tflops_sustained"]) / 2.0
+    except Exception:
+        tf32_peak = 1400.0 / 2.0
+    if world == 1 and not args.no_extras:
+        # (a) throughput regime of the C2 model: 65536 trials per step
+        Bt, Tt = C2_THROUGHPUT["trials_per_gpu"], C2_THROUGHPUT["T"]
+        mt = VJF.make_model(D, d, cfg["udim"], cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], max_trials=Bt, seed=99, device=dev)
+        mt.load_full_state(bench_state(cfg))
+        yt = lorenz_poisson(Tt, Bt, D, seed=2000).to(dev)
+        st_t = mt._flat.clone()
+
+        def step_t():
+            mt._flat.copy_(st_t)
+            mt.run(yt)
+        ms = time_runs(step_t, 5)
+        tps = Bt * Tt / (ms * 1e-3)
+        ach = ALGO_BYTES_PER_TRIAL_STEP(cfg) * tps / 1e9
+        fl = tensor_flops_per_trial_step(cfg)
+        extras["throughput_regime"] = {
+            "workload": f"{cfg['name']} shapes, {Bt} trials x {Tt} time steps per launch (Lorenz-driven counts), in-kernel Philox",
+            "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / Tt * 1e3, "kernel_kind": int(lib.vjf_last_launch_kind()),
+            "status_word": int(mt.status()),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+            "tensor_bound": {"tensor_flops_per_trial_step": fl, "achieved_tflops": fl * tps / 1e12, "peak_tflops": tf32_peak,
+                             "frac": fl * tps / 1e12 / tf32_peak,
+                             "note": "hi/lo tf32 operand pairs (three products per contraction) make this path tensor-bound before it is "
+                                     "HBM-bound: peak = MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)"}}
+        del mt, yt
+        # (b) one GPU's share of the C4 split over 8 GPUs (8192 trials, ydim 2000): the per-GPU work of the sharded benchmark
+        c4 = C4
+        B4, T4 = c4["global_trials"] // 8, c4["T"]
+        m4 = VJF.make_model(c4["ydim"], c4["xdim"], 0, c4["n_rbf"], c4["hidden"], c4["likelihood"], max_trials=B4, seed=99, device=dev)
+        m4.load_full_state(bench_state(c4))
+        y4 = synthetic_counts_gpu(T4, B4, c4["ydim"], c4["xdim"], dev, 31)
+        st4 = m4._flat.clone()
+
+        def step_4():
+            m4._flat.copy_(st4)
+            m4.run(y4)
+        ms = time_runs(step_4, 3)
+        tps = B4 * T4 / (ms * 1e-3)
+        ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / 1e9
+        extras["c4_one_gpu_share"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {B4} trials (1/8 of 65536) x {T4} steps",
+                                      "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4 * 1e3,
+                                      "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
+                                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+        del m4, y4
+    if world > 1 and not args.no_extras:
+        # C4 strong scaling: 65536 trials in all, sharded over the ranks (BASELINE.json configs[3])
+        from vjf_b200.distributed import ShardedVJF as _S
+        c4 = C4
+        B4, T4 = c4["global_trials"] // world, c4["T"]
+        m4 = VJF.make_model(c4["ydim"], c4["xdim"], 0, c4["n_rbf"], c4["hidden"], c4["likelihood"], max_trials=B4, seed=99, device=dev)
+        m4.load_full_state(bench_state(c4))
+        y4 = synthetic_counts_gpu(T4, B4, c4["ydim"], c4["xdim"], dev, 31 + rank)
+        st4 = m4._flat.clone()
+        r4 = _S(m4).connect()
+
+        def step_4():
+            m4._flat.copy_(st4)
+            r4.run(y4)
+        dist.barrier(); torch.cuda.synchronize()
+        ms = time_runs(step_4, 3)
+        t4 = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        ms = float(t4.item())
+        tps = c4["global_trials"] * T4 / (ms * 1e-3)
+        ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / world / 1e9
+        extras["c4_strong_scaling"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {c4['global_trials']} trials over {world} GPUs "
+                                                   f"({B4} per GPU) x {T4} steps, in-kernel NVLink all-reduce", "scaling": "strong",
+                                       "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4 * 1e3,
+                                       "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
+                                       "roofline_per_gpu": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+        del r4, m4, y4
+
     if world > 1:
         tt = torch.tensor([total_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -442,31 +621,37 @@ def run_ours(args, cfg):
     if rank == 0:
         units = B * world * T * args.steps
         value = units / (total_ms * 1e-3)
-        peak, peak_src = measured_peak_gbs()
-        algo_bytes = ALGO_BYTES_PER_TRIAL_STEP(cfg) * B * T  # per launch of the persistent kernel, per GPU
+        algo_bytes = ALGO_BYTES_PER_TRIAL_STEP(cfg) * B * T  # per launch of the time-loop kernel, per GPU
+        kname = "vjf_tile_kernel" if kind == 1 else "vjf_persistent_kernel"
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        tps = measured_traffic_per_time_step() if (cfg["trials_per_gpu"] == C2["trials_per_gpu"] and world == 1) else None
+        tps, tsrc = measured_traffic_per_time_step(kname) if (cfg["trials_per_gpu"] == C2["trials_per_gpu"] and world == 1) else (None, None)
         out = {"metric": "trial-steps/sec", "value": value, "unit": "trial-steps/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": DATA_DESC,
                "config": workload_config(cfg, world),
                "us_per_time_step": total_ms / args.steps / T * 1e3,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": (tps * T if tps else None), "traffic_source": "profiles/traffic_r01.json (ncu dram__bytes_read+write per time step) x T",
-                            "algorithmic_bytes_per_launch": algo_bytes, "kernel": "vjf_persistent_kernel",
+                            "traffic": (tps * T if tps else None), "traffic_source": (f"{tsrc} (ncu dram__bytes_read+write per time step) x T" if tsrc else None),
+                            "algorithmic_bytes_per_launch": algo_bytes, "kernel": kname,
                             "algorithmic_bytes_per_trial_step": ALGO_BYTES_PER_TRIAL_STEP(cfg), "peak_source": peak_src,
                             "note": "B=4096 trials/step is latency-bound by the per-step serial chain (grid barriers + RLS factorisation), see DESIGN.md"},
                "e2e": {"value": units / e2e_s, "unit": "trial-steps/s", "h2d_bytes_per_step": int(y_host.numel() * 4),
                        "d2h_bytes_per_step": int((mu_h.numel() + lv_h.numel() + ls_h.numel()) * 4),
-                       "api": "vjf_run_host (C ABI, pinned host buffers, chunked H2D overlapped with compute)"},
+                       "api": ("vjf_run_sharded_host" if world > 1 else "vjf_run_host") + " (C ABI, pinned host buffers, chunked H2D overlapped with compute)"},
                "gpu_launches": int(launches), "clocks": clocks, "status_word": int(status),
                "status_word_e2e": int(model.status())}
         if e2e_u8:
             out["e2e_u8"] = e2e_u8
+        out["kernel_kind"] = {"value": kind, "meaning": "1 = tile pipeline (tcgen05 on every contraction, TMA tensor loads), 0 = general persistent kernel"}
+        if parity is not None:
+            out["parity_check"] = parity
+        out.update(extras)
         if world == 1 and not args.no_cpu:
             if reference_available():
                 rr = ReferenceRunner(cfg, B, args.cpu_steps, 1)
+                rr.T_s = 8
                 rr.epoch()  # warm-up (thread pools, allocator)
+                rr.T_s = args.cpu_steps
                 dt = rr.epoch()
                 out["cpu_baseline"] = {"value": B * args.cpu_steps / dt, "unit": "trial-steps/s", "cores": os.cpu_count(),
                                        "kind": "reference", "sample": rr.describe(dt)}
@@ -489,9 +674,10 @@ def main():
     ap.add_argument("--T", type=int, default=None, help="time steps per bench step (default 256)")
     ap.add_argument("--chunk", type=int, default=16, help="time steps per H2D chunk in the e2e path (the uint8 variant uses 2x)")
     ap.add_argument("--spinup", type=float, default=1.0, help="seconds of extra untimed load so clocks leave idle")
-    ap.add_argument("--cpu-steps", type=int, default=24, help="time steps of the CPU baseline sample (~10-20 s of the reference)")
-    ap.add_argument("--ref-steps-per-step", type=int, default=8, help="--impl reference: time steps (a T-prefix of the workload) per bench step")
+    ap.add_argument("--cpu-steps", type=int, default=768, help="time steps of the CPU baseline sample (~10-20 s of the reference: the T-step workload repeated)")
+    ap.add_argument("--ref-steps-per-step", type=int, default=128, help="--impl reference: time steps (a T-prefix of the workload) per bench step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the further regimes (throughput regime, C4 share / strong scaling)")
     args = ap.parse_args()
     cfg = dict(C2)
     if args.trials:

@@ -159,6 +159,13 @@ int vjf_run_sharded(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_global,
                     uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu, float* logvar, float* losses,
                     void* stream);
 
+/* vjf_run_host for the local block of trials of a sharded run: chunked, double-buffered host->device copies of this rank's
+ * observations overlapped with the fused compute + exchange kernel of the previous chunk, device->host copies of the
+ * trajectory and losses.  All ranks must call it with the same T / chunk_steps / flags / lr. */
+int vjf_run_sharded_host(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_global, uint64_t trial_offset, const void* y_host,
+                         int32_t y_dtype, const float* u_host, const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags,
+                         float lr, float* mu_host, float* logvar_host, float* losses_host, int32_t chunk_steps);
+
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);
 
@@ -173,6 +180,10 @@ int64_t vjf_launch_count(void);
  * contraction on tcgen05, observations by TMA tensor copies), 0 = the general persistent kernel (shapes outside the tile plan:
  * several hidden layers, hidden width not a multiple of 32, uint8 observations, ...) */
 int32_t vjf_last_launch_kind(void);
+/* kernel selection of the time loop (process-wide; for tests and A/B timing): 0 automatic (default), 1 general persistent kernel
+ * only, 2 tile pipeline without its exact-observation mode, 3 tile pipeline with 64-trial tiles whenever the observations are
+ * exact in tf32 (spike counts) */
+int vjf_set_tile_mode(int32_t mode);
 
 /* ---- whole-trajectory RLS re-initialisation: RBFDS.initialize + LinearRegression.initialize
  * (vjf/model.py:379-388, vjf/module.py:144-150).  xs, xt [N][xdim], u [N][udim] or NULL; the caller

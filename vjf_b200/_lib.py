@@ -48,10 +48,12 @@ SIGNATURES = {
     "vjf_comm_local_handle": (C.c_int, [_P, _P]),
     "vjf_comm_connect": (C.c_int, [_P, _I32, _I32, _P]),
     "vjf_run_sharded": (C.c_int, [_P, _I32, _I32, _I32, _U64, _P, _I32, _P, _P, _P, _P, _U64, _U64, _U32, _F, _P, _P, _P, _P]),
+    "vjf_run_sharded_host": (C.c_int, [_P, _I32, _I32, _I32, _U64, _P, _I32, _P, _P, _U64, _U64, _U32, _F, _P, _P, _P, _I32]),
     "vjf_get_status": (C.c_int, [_P, _P, C.POINTER(_U32), _I32]),
     "vjf_philox_normal": (C.c_int, [_U64, _U64, _U64, _I32, _I32, _P, _P]),
     "vjf_launch_count": (_I64, []),
     "vjf_last_launch_kind": (_I32, []),
+    "vjf_set_tile_mode": (C.c_int, [_I32]),
     "vjf_rls_initialize": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "vjf_forecast": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vjf_kalman_predict_batched": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

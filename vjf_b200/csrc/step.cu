@@ -510,9 +510,10 @@ static int ensure(void** p, size_t* have, size_t need) {
   return 0;
 }
 
-extern "C" int vjf_run_host(vjf_handle* h, int32_t T, int32_t B, const void* y_host, int32_t y_dtype, const float* u_host,
-                            const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu_host,
-                            float* logvar_host, float* losses_host, int32_t chunk_steps) {
+// sharded != 0: the chunks run through vjf_run_sharded (trials of this rank; B_global / trial_offset as there)
+static int run_host_impl(vjf_handle* h, int sharded, int32_t T, int32_t B, int32_t B_global, uint64_t trial_offset, const void* y_host,
+                         int32_t y_dtype, const float* u_host, const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags, float lr,
+                         float* mu_host, float* logvar_host, float* losses_host, int32_t chunk_steps) {
   if (!h || !y_host || !mu_host || !logvar_host) { vjf_set_error("null argument"); return -1; }
   if (h->cfg.udim > 0 && !u_host) { vjf_set_error("udim=%d but u is NULL", h->cfg.udim); return -1; }
   if (!(flags & VJF_FLAG_PRIOR_Q0)) { vjf_set_error("vjf_run_host starts from the prior: set VJF_FLAG_PRIOR_Q0"); return -1; }
@@ -561,10 +562,12 @@ extern "C" int vjf_run_host(vjf_handle* h, int32_t T, int32_t B, const void* y_h
       VJF_CUDA_OK(cudaMemcpyAsync(lv_d, h->stage_lv + ((size_t)pb * (C + 1) + pn) * B * d, (size_t)B * d * 4, cudaMemcpyDeviceToDevice, ks));
     }
     const uint32_t fl = (c == 0) ? flags : (flags & ~(uint32_t)VJF_FLAG_PRIOR_Q0);
-    if (vjf_run(h, n, B, h->stage_y[buf], y_dtype, u ? h->stage_u[buf] : nullptr, mu_d, lv_d,
-                eps_host ? h->stage_eps[buf] : nullptr, seed, step0 + t0, fl, lr, mu_d + (size_t)B * d, lv_d + (size_t)B * d,
-                loss_d, ks))
-      return -2;
+    const int rc = sharded
+        ? vjf_run_sharded(h, n, B, B_global, trial_offset, h->stage_y[buf], y_dtype, u ? h->stage_u[buf] : nullptr, mu_d, lv_d,
+                          eps_host ? h->stage_eps[buf] : nullptr, seed, step0 + t0, fl, lr, mu_d + (size_t)B * d, lv_d + (size_t)B * d, loss_d, ks)
+        : vjf_run(h, n, B, h->stage_y[buf], y_dtype, u ? h->stage_u[buf] : nullptr, mu_d, lv_d, eps_host ? h->stage_eps[buf] : nullptr, seed,
+                  step0 + t0, fl, lr, mu_d + (size_t)B * d, lv_d + (size_t)B * d, loss_d, ks);
+    if (rc) return -2;
     VJF_CUDA_OK(cudaMemcpyAsync(mu_host + (size_t)t0 * B * d, mu_d + (size_t)B * d, (size_t)n * B * d * 4, cudaMemcpyDeviceToHost, ks));
     VJF_CUDA_OK(cudaMemcpyAsync(logvar_host + (size_t)t0 * B * d, lv_d + (size_t)B * d, (size_t)n * B * d * 4, cudaMemcpyDeviceToHost, ks));
     if (losses_host) VJF_CUDA_OK(cudaMemcpyAsync(losses_host + (size_t)t0 * 4, loss_d, (size_t)n * 16, cudaMemcpyDeviceToHost, ks));
@@ -573,4 +576,18 @@ extern "C" int vjf_run_host(vjf_handle* h, int32_t T, int32_t B, const void* y_h
   VJF_CUDA_OK(cudaStreamSynchronize(ks));
   VJF_CUDA_OK(cudaStreamSynchronize(cs));
   return 0;
+}
+
+extern "C" int vjf_run_host(vjf_handle* h, int32_t T, int32_t B, const void* y_host, int32_t y_dtype, const float* u_host,
+                            const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags, float lr, float* mu_host,
+                            float* logvar_host, float* losses_host, int32_t chunk_steps) {
+  return run_host_impl(h, 0, T, B, B, 0, y_host, y_dtype, u_host, eps_host, seed, step0, flags, lr, mu_host, logvar_host, losses_host, chunk_steps);
+}
+
+extern "C" int vjf_run_sharded_host(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_global, uint64_t trial_offset, const void* y_host,
+                                    int32_t y_dtype, const float* u_host, const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags,
+                                    float lr, float* mu_host, float* logvar_host, float* losses_host, int32_t chunk_steps) {
+  if (!h || h->comm_world < 1) { vjf_set_error("vjf_comm_connect has not been called"); return -1; }
+  return run_host_impl(h, 1, T, B_local, B_global, trial_offset, y_host, y_dtype, u_host, eps_host, seed, step0, flags, lr, mu_host, logvar_host,
+                       losses_host, chunk_steps);
 }

@@ -10,6 +10,15 @@
 
 static inline int rup(int v, int a) { return (v + a - 1) / a * a; }
 
+// 0: automatic; 1: never use the tile pipeline; 2: tile pipeline without the exact-observation mode; 3: 64-trial tiles whenever
+// the observations are exact (tests drive every variant through the same process)
+static int g_tile_mode = 0;
+extern "C" int vjf_set_tile_mode(int32_t mode) {
+  if (mode < 0 || mode > 3) { vjf_set_error("tile mode must be 0..3"); return -1; }
+  g_tile_mode = mode;
+  return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_fn() {
@@ -94,20 +103,21 @@ int vjf_tile_create(vjf_handle* h) {
 int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map, cudaStream_t stream) {
   static const bool disabled = getenv("VJF_B200_NO_TILE") != nullptr;
   p.tp.on = 0;
-  if (disabled || !h->w1k || y_dtype != VJF_Y_F32 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 || h->num_sms < 2 || !encode_fn()) return 0;
+  if (disabled || g_tile_mode == 1 || !h->w1k || y_dtype != VJF_Y_F32 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 || h->num_sms < 2 || !encode_fn()) return 0;
   TilePlan pl;
   memset(&pl, 0, sizeof(pl));
   if (!tile_static_dims(p, pl)) return 0;
   const int H = p.H[0], d = p.d, D = p.D;
   static const int force_tbr = getenv("VJF_B200_TILE_ROWS") ? atoi(getenv("VJF_B200_TILE_ROWS")) : 0;
-  static const bool no_exact = getenv("VJF_B200_NO_EXACT") != nullptr;
+  static const bool no_exact_env = getenv("VJF_B200_NO_EXACT") != nullptr;
+  const bool no_exact = no_exact_env || g_tile_mode == 2;
   // spike counts (Poisson likelihood): are they exact in tf32?
   bool exact = false;
   if (p.lik == VJF_LIK_POISSON && !no_exact && observations_exact(h, y, (size_t)T * B * D, stream, &exact)) return -1;
   pl.CL0 = exact ? D / 32 : 0;
   pl.NBLKLO = pl.NBLK - pl.CL0 / 4;  // lo accumulator blocks, aligned with the blocks CL0 / 4 .. of the hi part
   // tiles of 32 trials; 64 when the lo image is small (exact observations) and every trial CTA gets more than one tile
-  pl.TBR = force_tbr ? force_tbr : ((exact && (B + 31) / 32 > h->max_slots - 1) ? 64 : 32);
+  pl.TBR = force_tbr ? force_tbr : ((exact && ((B + 31) / 32 > h->max_slots - 1 || g_tile_mode == 3)) ? 64 : 32);
   // one tile per trial CTA (latency regime): the second observation buffer would never be used -- its space goes to the
   // weight ring instead (deeper prefetch of the layer-1 weight chunks)
   const int ntiles = (B + pl.TBR - 1) / pl.TBR;
@@ -156,7 +166,7 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   // scratch of the per-step flush (register accumulators of 15 warps) and workspace of the shared phases B1 / B2
   const int DX = d <= 2 ? 2 : (d == 3 ? 3 : (d == 4 ? 4 : 8));
   const int flush_floats = TK_NCW * (DX + 1) * 32 + TK_NCW * 2 * pl.HC * DX * 32 + 16 * VJF_NSCAL + 16 + 16;
-  if (flush_floats * 4 > pl.o_uk - pl.o_pg) return 0;
+  if (flush_floats * 4 > pl.scratch_bytes) return 0;
   size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) return 0;
   const int s_b1 = (int)((b2 + 3) & ~(size_t)3);

@@ -741,7 +741,7 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
   const int D = p.D, d = p.d, R = p.R, H = p.H[0];
   float* slot = p.partials + (size_t)blockIdx.x * p.PS;
   float* sf = reinterpret_cast<float*>(sb + pl.o_f);
-  float* scr = reinterpret_cast<float*>(sb + pl.o_pg);  // scratch: the phi / g_pre region + weight ring (dead between steps)
+  float* scr = reinterpret_cast<float*>(sb + pl.o_in[0]);  // scratch: everything up to the [w_chol ; w_mean] images is dead between steps
   if (!have_tiles) {
     #pragma unroll 1
     for (int i = tid; i < p.PS; i += VJF_NT) slot[i] = 0.f;

@@ -78,14 +78,11 @@ class ShardedVJF:
         """y: (T, B_local, ydim) on this rank's device.  Returns mu, logvar (T, B_local, d), losses (T, 4)
         (losses are whole-job values, identical on every rank)."""
         m, lib = self.m, self.m._lib
-        y = y if y.dtype == torch.uint8 else y.to(m.device, torch.float32)
+        y = y.to(m.device) if y.dtype == torch.uint8 else y.to(m.device, torch.float32)
         ydt = _lib.Y_U8 if y.dtype == torch.uint8 else _lib.Y_F32
         T, B, _ = y.shape
-        nb = torch.tensor([B], device=m.device)
-        if self.world > 1:
-            dist.all_reduce(nb, group=self.group)
-        Bg = int(nb.item())
-        off = self.rank * B if trial_offset is None else trial_offset
+        Bg, off0 = self._global_batch(B)
+        off = off0 if trial_offset is None else trial_offset
         mu = torch.empty(T, B, m.xdim, device=m.device)
         lv = torch.empty_like(mu)
         losses = torch.empty(T, 4, device=m.device)
@@ -111,9 +108,31 @@ class ShardedVJF:
         m._step_index += T
         return mu, lv, losses
 
+    def _global_batch(self, B):
+        """(total trials over all ranks, first global trial index of this rank): an exclusive prefix sum over the ranks'
+        block sizes, so that uneven blocks (shard_bounds gives the last ranks smaller ones) keep disjoint Philox trial ids."""
+        if self.world == 1:
+            return B, 0
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.m.device)
+        sizes[self.rank] = B
+        dist.all_reduce(sizes, group=self.group)
+        sizes = sizes.tolist()
+        return int(sum(sizes)), int(sum(sizes[:self.rank]))
+
     @torch.no_grad()
-    def run_host(self, y_host, mu_host, lv_host, losses_host):
-        y = y_host.to(self.m.device, non_blocking=True)
-        mu, lv, losses = self.run(y)
-        mu_host.copy_(mu, non_blocking=True); lv_host.copy_(lv, non_blocking=True); losses_host.copy_(losses, non_blocking=True)
-        torch.cuda.synchronize()
+    def run_host(self, y_host, mu_host, lv_host, losses_host, *, chunk_steps=16, sgd=True, update=True, warm_up=False):
+        """End-to-end sharded run from (pinned) host buffers through the C ABI entry vjf_run_sharded_host: chunked,
+        double-buffered H2D of this rank's observations overlapped with the fused compute + exchange kernel."""
+        m, lib = self.m, self.m._lib
+        assert self.fused and self.world > 1, "connect() first (peer-memory exchange)"
+        ydt = _lib.Y_U8 if y_host.dtype == torch.uint8 else _lib.Y_F32
+        T, B, _ = y_host.shape
+        Bg, off = self._global_batch(B)
+        frozen = not m.decoder.decode.weight.requires_grad
+        f = plan_step(0, sgd, update, warm_up, frozen)
+        p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        torch.cuda.current_stream(m.device).synchronize()
+        with torch.cuda.device(m.device):
+            _lib.check(lib.vjf_run_sharded_host(m._h, T, B, Bg, off, p(y_host), ydt, None, None, m.seed, m._step_index, f, m.lr,
+                                                p(mu_host), p(lv_host), p(losses_host), chunk_steps))
+        m._step_index += T
