@@ -191,6 +191,14 @@ int vjf_set_tile_mode(int32_t mode);
  * samples instead of the reference's (N,N) temporary. */
 int vjf_rls_initialize(vjf_handle* h, int64_t N, const float* xs, const float* xt, const float* u, void* stream);
 
+/* ---- weight-space Kalman update with diffusion: LinearRegression.kalman (vjf/module.py:114-142) = kalman.predict with A = I,
+ * Q = diffusion * I followed by kalman.joseph_update AS WRITTEN (vjf/kalman.py:102-145) with H = features of [xs, u] and
+ * R = v * I.  xs [N][xdim], u [N][udim] or NULL, target [N][xdim].  Updates w_mean and w_chol (lower Cholesky factor of the
+ * posterior weight covariance) in `state`.  Evaluated in information form from the streamed statistics phi^T phi, phi^T target:
+ * no N x N innovation covariance. */
+int vjf_weight_kalman(vjf_handle* h, int64_t N, const float* xs, const float* target, const float* u, float v, float diffusion,
+                      void* stream);
+
 /* ---- forecast: RBFDS.forecast with sampled weights (vjf/model.py:342-361, module.py:70-73).
  * x [n_step+1][B][xdim] (x[0] given), yhat [n_step+1][B][ydim] or NULL, w_eps [n_step][R][xdim],
  * x_eps [n_step][B][xdim] or NULL (noise=False). */

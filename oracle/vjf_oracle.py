@@ -425,6 +425,55 @@ class OracleVJF:
                 x[t + 1] = x[t + 1] + np.asarray(x_eps[t], dt) * s
         return x, x @ self.dec_w.T + self.dec_b
 
+    def weight_kalman(self, xu, target, v, diffusion=0.0):
+        """LinearRegression.kalman vjf/module.py:114-142: weight-space Kalman update with A = I, Q = diffusion * I,
+        H = features (sample, feature), R = v * I_sample, through kalman.predict (vjf/kalman.py:15-50) and
+        kalman.joseph_update AS WRITTEN (:102-145, S^-1 applied twice).  S is (sample, sample) here, like the reference."""
+        dt = self.dtype
+        assert diffusion >= 0.0, "diffusion needs to be non-negative"
+        eye = np.eye(self.n_rbf, dtype=dt)
+        H = self.feature(np.asarray(xu, dt))
+        R = np.eye(H.shape[0], dtype=dt) * dt.type(v)
+        yhat, mhat, Lhat = kalman_predict(self.w_mean, self.w_chol, eye, dt.type(diffusion) * eye, H)
+        self.w_mean, self.w_chol = kalman_joseph_update(np.asarray(target, dt), yhat, mhat, Lhat, H, R)
+
+    def fit(self, y, u=None, *, eps, centroid_unit, max_iter=200, beta=0.1, rtol=1e-4):
+        """VJF.fit vjf/model.py:223-307: epochs over the sequence; warm-up exit (:278-292: decoder freeze, transition
+        re-initialisation from the filtered means), convergence break (:293-296), running loss (:298), per-epoch lr decay
+        (:303).  eps: (max_iter, T, 2, B, d) noise tape; centroid_unit(r) -> (R, d+u) centroids drawn U(-r, r).
+        Returns mu, logvar, epoch_loss, n_epochs run."""
+        dt = self.dtype
+        y = np.asarray(y, dt)
+        if y.ndim == 2:
+            y = y[:, None, :]
+        T = y.shape[0]
+        warm_up = True
+        running = float("nan")
+        epoch_loss = float("nan")
+        isclose = lambda a, b: bool(np.isfinite(a) and np.isfinite(b) and abs(a - b) <= 1e-8 + rtol * abs(b))  # torch.isclose
+        n_epochs = 0
+        mu = lv = None
+        for i in range(max_iter):
+            mu, lv, losses = self.run(y, u, eps=eps[i], warm_up=warm_up)
+            n_epochs += 1
+            epoch_loss = dt.type(np.sum(losses[:, 0], dtype=dt) / dt.type(T))
+            if warm_up:
+                if isclose(epoch_loss, running):
+                    warm_up = False
+                    running = epoch_loss
+                    self.decoder_frozen = True
+                    u_init = None if (u is None or self.udim == 0) else np.asarray(u, dt)[1:].reshape(-1, self.udim)
+                    xt_, xs_ = mu[1:].reshape(-1, self.xdim), mu[:-1].reshape(-1, self.xdim)
+                    xu = xs_ if u_init is None else np.concatenate([xs_, u_init], -1)
+                    r = float(np.sqrt((xu * xu).sum(1)).max())
+                    self.initialize_transition(xt_, xs_, u_init, centroid=centroid_unit(r))
+            else:
+                if isclose(epoch_loss, running):
+                    break
+            running = beta * running + (1 - beta) * epoch_loss if i > 0 else epoch_loss
+            self.lr *= self.lr_decay
+        return mu, lv, epoch_loss, n_epochs
+
 
 # --------------------------------------------------------------------------------------------
 # Kalman operator (vjf/kalman.py, vjf/numerical.py) -- single problem, (n,batch) state layout

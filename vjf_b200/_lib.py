@@ -55,6 +55,7 @@ SIGNATURES = {
     "vjf_last_launch_kind": (_I32, []),
     "vjf_set_tile_mode": (C.c_int, [_I32]),
     "vjf_rls_initialize": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "vjf_weight_kalman": (C.c_int, [_P, _I64, _P, _P, _P, _F, _F, _P]),
     "vjf_forecast": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vjf_kalman_predict_batched": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vjf_kalman_update_batched": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -43,6 +43,12 @@ class _Velocity(_Holder):
     def forward(self, x, sampling=True):
         return self._owner._velocity(x, sampling)
 
+    def kalman(self, x, target, v, diffusion: float = 0.):
+        """LinearRegression.kalman (vjf/module.py:114-142): weight-space Kalman update; x: (sample, xdim + udim) inputs
+        of the features, target: (sample, xdim), v: observation-noise variance, Q = diffusion * I."""
+        assert diffusion >= 0., 'diffusion needs to be non-negative'  # module.py:127
+        return self._owner._weight_kalman(x, target, v, diffusion)
+
 
 class _Scheduler:
     """ExponentialLR stand-in (vjf/model.py:78, :303)."""
@@ -211,6 +217,41 @@ class VJF(nn.Module):
         if "w_pchol" not in s and "w_precision" in s:
             self.w_pchol.copy_(torch.linalg.cholesky(self.w_precision.double()).float())
 
+    def save(self, path):
+        """On-disk checkpoint: everything a resumed fit needs -- parameters, the RLS state the reference keeps outside
+        state_dict() (vjf/module.py:50-54), the sample counters, the learning rate after the decays so far (vjf/model.py:78, :303),
+        the decoder freeze (:283) and the position in the Philox noise stream."""
+        torch.save({"format": "vjf_b200/1",
+                    "config": dict(ydim=self.ydim, xdim=self.xdim, udim=self.udim, n_rbf=self.n_rbf, hidden_sizes=self.hidden_sizes,
+                                   likelihood=self.likelihood_name),
+                    "state": {k: v.cpu() for k, v in self.full_state().items()},
+                    "lr": self.lr, "lr_decay": self.scheduler.gamma, "step_index": self._step_index, "seed": self.seed,
+                    "decoder_frozen": not self.decoder.decode.weight.requires_grad}, path)
+
+    def load(self, path):
+        """Restore a checkpoint written by save() into this model (same configuration required)."""
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        if ck.get("format") != "vjf_b200/1":
+            raise RuntimeError(f"{path}: not a vjf_b200 checkpoint")
+        mine = dict(ydim=self.ydim, xdim=self.xdim, udim=self.udim, n_rbf=self.n_rbf, hidden_sizes=self.hidden_sizes,
+                    likelihood=self.likelihood_name)
+        if ck["config"] != mine:
+            raise RuntimeError(f"{path}: checkpoint of {ck['config']}, this model is {mine}")
+        self.load_full_state(ck["state"])
+        self.optimizer.param_groups[0]["lr"] = float(ck["lr"])
+        self.scheduler.gamma = float(ck["lr_decay"])
+        self._step_index, self.seed = int(ck["step_index"]), int(ck["seed"])
+        self.decoder.requires_grad_(not ck["decoder_frozen"])
+        return self
+
+    @classmethod
+    def from_checkpoint(cls, path, **kwargs):
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        c = ck["config"]
+        m = cls(c["ydim"], c["xdim"], c["udim"], c["n_rbf"], c["hidden_sizes"], c["likelihood"], lr=ck["lr"], lr_decay=ck["lr_decay"],
+                **kwargs)
+        return m.load(path)
+
     @property
     def n_sample(self):
         return int(self._flat[self._lay.tr_n].item())
@@ -363,10 +404,12 @@ class VJF(nn.Module):
 
     @torch.no_grad()
     def fit(self, y, u=None, *, max_iter: int = 200, beta: float = 0.1, verbose: bool = False, rtol: float = 1e-4,
-            progress: bool = True):
+            progress: bool = True, eps=None, init_centroid=None):
         """Same contract as the reference's VJF.fit (vjf/model.py:223-307): epochs over the sequence with a
         warm-up phase, decoder freeze + RLS re-initialisation when the warm-up loss settles, per-epoch lr
-        decay, convergence test on the running loss.  Returns (mu, logvar, epoch_loss)."""
+        decay, convergence test on the running loss.  Returns (mu, logvar, epoch_loss).
+        Extensions for reproducible tests: ``eps`` (max_iter, T, 2, B, xdim) noise tape instead of the in-kernel Philox stream,
+        ``init_centroid`` the centroids RBFDS.initialize would re-draw (vjf/module.py:147)."""
         y = torch.as_tensor(y)
         y = y.to(self.device) if y.dtype == torch.uint8 else y.to(self.device, torch.float32)
         y = torch.atleast_2d(y)
@@ -392,7 +435,7 @@ class VJF(nn.Module):
                 pass
         mu = lv = None
         for i in it:
-            mu, lv, losses = self.run(y, u_, None, sgd=True, update=True, warm_up=warm_up)
+            mu, lv, losses = self.run(y, u_, None, sgd=True, update=True, warm_up=warm_up, eps=None if eps is None else eps[i])
             epoch_loss = losses[:, 0].mean().cpu()
             self.status()
             if warm_up:
@@ -402,7 +445,8 @@ class VJF(nn.Module):
                     print("\nWarm up stopped.\n")
                     self.decoder.requires_grad_(False)  # freeze decoder after warm up (model.py:283)
                     u_init = u_[1:].reshape(-1, u_.shape[-1]) if (u_ is not None and u_.shape[-1] > 0) else None
-                    self.initialize_transition(mu[1:].reshape(-1, self.xdim), mu[:-1].reshape(-1, self.xdim), u_init)
+                    self.initialize_transition(mu[1:].reshape(-1, self.xdim), mu[:-1].reshape(-1, self.xdim), u_init,
+                                               centroid=init_centroid)
             else:
                 if torch.isclose(epoch_loss, running_loss, rtol=rtol):
                     print("\nConverged.\n")
@@ -478,6 +522,16 @@ class VJF(nn.Module):
             _lib.check(self._lib.vjf_forecast(self._h, n_step, B, _ptr(x), _ptr(yhat), _ptr(u), _ptr(w_eps), _ptr(x_eps),
                                               self._stream()))
         return x, yhat
+
+    @torch.no_grad()
+    def _weight_kalman(self, x, target, v, diffusion):
+        x = torch.atleast_2d(torch.as_tensor(x).to(self.device, torch.float32))
+        target = torch.atleast_2d(torch.as_tensor(target).to(self.device, torch.float32)).contiguous()
+        xs = x[:, :self.xdim].contiguous()
+        u = x[:, self.xdim:].contiguous() if self.udim > 0 else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.vjf_weight_kalman(self._h, xs.shape[0], _ptr(xs), _ptr(target), _ptr(u), float(v), float(diffusion),
+                                                   self._stream()))
 
     @torch.no_grad()
     def _velocity(self, x, sampling=True):
