@@ -35,6 +35,9 @@ C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[
 # BASELINE.json configs[3]: neural-population scale, 65536 trials sharded over the GPUs (strong scaling), SURVEY.md 8d row C4
 C4 = dict(name="C4-population-poisson", ydim=2000, xdim=8, udim=0, n_rbf=64, hidden=[128], likelihood="poisson",
           global_trials=65536, T=8)
+# BASELINE.json configs[4]: long-horizon latency path: 1024 trials, T = 100 000, Gaussian observations
+C5 = dict(name="C5-long-horizon-gaussian", ydim=50, xdim=4, udim=0, n_rbf=32, hidden=[32], likelihood="gaussian",
+          trials_per_gpu=1024, T=100000)
 # the same C2 model in the throughput regime: enough trials per step that the serial part of a step is amortised
 C2_THROUGHPUT = dict(trials_per_gpu=65536, T=16)
 DATA_DESC = "synthetic (Lorenz-driven Poisson counts, random-init parameters; CPU-seeded, identical for both arms)"
@@ -334,6 +337,24 @@ def synthetic_counts_gpu(T, B, D, d, dev, seed):
     return torch.poisson(torch.exp(torch.clamp(x @ Cm - 1.0, max=3.0)), generator=g)
 
 
+def limit_cycle_gaussian(t0, T, B, D, dev, seed):
+    """a 4-D latent made of two limit cycles (periods 63 and 41 steps, per-trial phases, slow amplitude
+    modulation), linear-Gaussian observations y = x C + b + 0.1 N(0,1).  Closed form in the time index, so any window
+    [t0, t0 + T) of the 100 000-step sequence can be generated on the device without holding the rest."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    ph = torch.rand(1, B, 2, device=dev, generator=g) * 6.283185
+    Cm = torch.randn(4, D, device=dev, generator=g) * 0.5
+    b = torch.randn(D, device=dev, generator=g)
+    t = (t0 + torch.arange(T, device=dev, dtype=torch.float64))[:, None, None]
+    w = torch.tensor([6.283185307 / 63.0, 6.283185307 / 41.0], device=dev, dtype=torch.float64)
+    th = (t * w + ph.double())
+    amp = 1.0 + 0.2 * torch.sin(t * (6.283185307 / 977.0) + ph.double()[..., :1])
+    x = torch.cat((amp * torch.cos(th), amp * torch.sin(th)), -1).float()  # (T, B, 4)
+    gn = torch.Generator(device=dev).manual_seed(seed + 1 + t0)
+    return x @ Cm + b + 0.1 * torch.randn(T, B, D, device=dev, generator=gn)
+
+
 def time_runs(fn, reps):
     """Mean CUDA-event time (ms) of fn() over reps calls, after one warm-up call."""
     import torch
@@ -585,6 +606,33 @@ def run_ours(args, cfg):
                                       "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
                                       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
         del m4, y4
+    if world == 1 and not args.no_extras:
+        # (c) C5, the long-horizon latency path: 1024 trials, Gaussian observations, consecutive time steps with NO state reset,
+        #     double-precision RLS (vjf_set_rls_precision(64)); observations generated window by window on the device
+        c5 = C5
+        B5, T5, W5 = c5["trials_per_gpu"], args.c5_steps, 10000
+        for bits in (64, 32):
+            m5 = VJF.make_model(c5["ydim"], c5["xdim"], 0, c5["n_rbf"], c5["hidden"], c5["likelihood"], max_trials=B5, seed=99, device=dev,
+                                rls_precision=bits)
+            m5.load_full_state(bench_state(c5))
+            q5, ms5, st5 = None, 0.0, 0
+            for c0 in range(0, T5, W5):
+                y5 = limit_cycle_gaussian(c0, min(W5, T5 - c0), B5, c5["ydim"], dev, seed=7)
+                a5 = torch.cuda.Event(enable_timing=True); b5 = torch.cuda.Event(enable_timing=True)
+                a5.record()
+                mu5, lv5, ls5 = m5.run(y5, None, q5)
+                b5.record(); torch.cuda.synchronize()
+                ms5 += a5.elapsed_time(b5)
+                q5 = (mu5[-1].clone(), lv5[-1].clone())
+                from vjf_b200.model import Gaussian as _G
+                q5 = _G(*q5)
+                st5 |= int(m5.status())
+            extras["c5_long_horizon" if bits == 64 else "c5_long_horizon_fp32_rls"] = {
+                "workload": f"{c5['name']}: xdim 4 ydim 50 gaussian n_rbf 32 hidden [32], {B5} trials, {T5} consecutive time steps, no state reset, "
+                            f"in-kernel Philox, RLS in fp{bits}", "us_per_time_step": ms5 / T5 * 1e3, "time_steps_per_s": T5 / (ms5 * 1e-3),
+                "value": B5 * T5 / (ms5 * 1e-3), "unit": "trial-steps/s", "status_word": st5, "final_loss": float(ls5[:, 0].mean().item()),
+                "kernel_kind": int(lib.vjf_last_launch_kind()), "note": "latency-bound path (SURVEY 8d): report us/step"}
+            del m5
     if world > 1 and not args.no_extras:
         # C4 strong scaling: 65536 trials in all, sharded over the ranks (BASELINE.json configs[3])
         from vjf_b200.distributed import ShardedVJF as _S
@@ -677,6 +725,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=768, help="time steps of the CPU baseline sample (~10-20 s of the reference: the T-step workload repeated)")
     ap.add_argument("--ref-steps-per-step", type=int, default=128, help="--impl reference: time steps (a T-prefix of the workload) per bench step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--c5-steps", type=int, default=100000, help="time steps of the C5 long-horizon entry")
     ap.add_argument("--no-extras", action="store_true", help="skip the further regimes (throughput regime, C4 share / strong scaling)")
     args = ap.parse_args()
     cfg = dict(C2)

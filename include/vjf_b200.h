@@ -166,6 +166,12 @@ int vjf_run_sharded_host(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_gl
                          int32_t y_dtype, const float* u_host, const float* eps_host, uint64_t seed, uint64_t step0, uint32_t flags,
                          float lr, float* mu_host, float* logvar_host, float* losses_host, int32_t chunk_steps);
 
+/* Precision of the recursive least squares (LinearRegression.rls, vjf/module.py:79-112): 32 (default; the reference's default
+ * dtype) or 64.  With 64 the accumulated w_precision is shadowed in double and the factorisation runs in double: the reference
+ * reaches that robustness by switching the whole model to float64 (script/example.py:12); the fp32 recursion stops absorbing
+ * samples and its Cholesky fails after ~1e7 samples (VJF_ST_CHOL_FAILED).  Needed for long horizons (T = 100 000). */
+int vjf_set_rls_precision(vjf_handle* h, int32_t bits);
+
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);
 

@@ -1,0 +1,95 @@
+"""Long horizons (BASELINE.json configs[4], "C5": T = 100 000, 1024 trials): thousands of consecutive steps with NO state reset
+against the fp64 oracle, and the double-precision RLS (vjf_set_rls_precision) where the fp32 recursion breaks down.
+Needs a B200: pytest -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from bench import C2, C5, bench_state, limit_cycle_gaussian, lorenz_poisson
+from oracle.vjf_oracle import OracleVJF
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_c5_shapes_2000_steps_match_fp64_oracle(bits):
+    """2000 consecutive filter + learning steps at the C5 shapes (xdim 4, ydim 50 Gaussian, 32 RBFs, hidden [32]) in ONE persistent
+    launch, shared noise tape, against the fp64 oracle run of the same sequence: trajectory, losses and every parameter at the
+    fp32 run tolerance (measured: 2e-5 on the means after 2000 steps)."""
+    from vjf_b200.model import VJF
+    dev = torch.device("cuda")
+    B, T = 64, 2000
+    y = limit_cycle_gaussian(0, T, B, C5["ydim"], dev, seed=7)
+    eps = torch.randn(T, 2, B, C5["xdim"], generator=torch.Generator().manual_seed(1))
+    m = VJF.make_model(C5["ydim"], C5["xdim"], 0, C5["n_rbf"], C5["hidden"], "gaussian", max_trials=B, seed=3, rls_precision=bits, lr=1e-3)
+    m.load_full_state(bench_state(C5))
+    mu, lv, ls = m.run(y, None, None, eps=eps)
+    assert m.status() == 0
+    o = OracleVJF(C5["ydim"], C5["xdim"], 0, C5["n_rbf"], C5["hidden"], "gaussian", dtype=np.float64, lr=1e-3)
+    s0 = o.get_state(); s0.update({k: v.numpy() for k, v in bench_state(C5).items()}); o.set_state(s0)
+    omu, olv, ols = o.run(y.cpu().numpy().astype(np.float64), eps=eps.numpy().astype(np.float64))
+    assert o.status == 0
+    tol = dict(rtol=2e-3, atol=2e-4)
+    assert_close(mu.cpu().numpy(), omu, what="mu", **tol)
+    assert_close(lv.cpu().numpy(), olv, what="logvar", **tol)
+    assert_close(ls.cpu().numpy(), ols, rtol=2e-3, atol=2e-3, what="losses")
+    got = {k: v.detach().cpu().numpy() for k, v in m.full_state().items()}
+    want = o.get_state()
+    for k in ("transition.logvar", "likelihood.logvar", "w_precision", "recognition.mlp.0.weight", "recognition.mean.weight",
+              "recognition.logvar.weight", "decoder.decode.weight", "decoder.decode.bias"):
+        assert_close(got[k], want[k], what=k, **tol)
+    # the RLS weights: tight with the double-precision recursion, conditioning-limited in fp32
+    wtol = dict(rtol=1e-3, atol=2e-4) if bits == 64 else dict(rtol=2e-2, atol=1e-2)
+    assert_close(got["w_mean"], want["w_mean"], what="w_mean", **wtol)
+    assert got["likelihood.n_sample"] == want["likelihood.n_sample"] and got["transition.n_sample"] == want["transition.n_sample"]
+
+
+def test_fp64_rls_solves_an_ill_conditioned_initialisation_fp32_cannot():
+    """RBFDS.initialize on few samples with overlapping RBFs: phi^T phi is close to singular.  In fp32 the factorisation either
+    fails (Cholesky pivot <= 0 -> 'RLS failed.'; the reference's fp32 fallback calls the removed torch.eig, vjf/module.py:104-112)
+    or returns weights far from the fp64 solution; the double-precision recursion matches the fp64 oracle's predictions."""
+    import warnings
+    from vjf_b200.model import VJF
+    dev = torch.device("cuda")
+    R, d, N = 50, 3, 64
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randn(N, d, generator=g); xt = xs + 0.1 * torch.randn(N, d, generator=g)
+    cen = torch.rand(R, d, generator=g) * 4 - 2
+    o = OracleVJF(50, d, 0, R, [32], "gaussian", dtype=np.float64)
+    o.initialize_transition(xt.numpy().astype(np.float64), xs.numpy().astype(np.float64), centroid=cen.numpy().astype(np.float64))
+    phi = o.feature(xs.numpy().astype(np.float64))
+    want = phi @ o.w_mean
+    err, status = {}, {}
+    for bits in (32, 64):
+        m = VJF.make_model(50, d, 0, R, [32], "gaussian", max_trials=64, rls_precision=bits)
+        m.initialize_transition(xt.to(dev), xs.to(dev), centroid=cen.to(dev))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            status[bits] = m.status()
+        err[bits] = float(np.abs(phi @ m.w_mean.cpu().numpy().astype(np.float64) - want).max())
+        if bits == 64:
+            assert_close(m.transition.logvar.item(), o.tr_logvar, 1e-3, 1e-3, "transition.logvar")
+    assert status[64] == 0 and err[64] < 1e-4 * max(1.0, float(np.abs(want).max())), (status, err)
+    assert (status[32] & 16) or err[32] > 10 * err[64], (status, err)
+
+
+def test_fp64_rls_keeps_the_weights_bounded_over_6000_steps_at_bench_scale():
+    """C2 at 4096 trials per step, 24 epochs of 256 steps without a reset (2.5e7 samples into the recursion): w_precision reaches
+    1e8.  The double-precision RLS stays well-behaved (status 0, |W| bounded); the fp32 recursion drifts (|W| several times
+    larger) -- the reason bench.py resets the state between its fp32 timing epochs."""
+    from vjf_b200.model import VJF
+    dev = torch.device("cuda")
+    y = lorenz_poisson(256, 4096, 200, seed=1000).to(dev)
+    wmax = {}
+    for bits in (32, 64):
+        m = VJF.make_model(200, 3, 0, 50, [64], "poisson", max_trials=4096, seed=99, rls_precision=bits)
+        m.load_full_state(bench_state(C2))
+        for ep in range(24):
+            mu, lv, ls = m.run(y)
+        assert torch.isfinite(ls).all()
+        wmax[bits] = m.w_mean.abs().max().item()
+        if bits == 64:
+            assert m.status() == 0
+            assert m.w_precision.abs().max().item() > 5e7
+    assert wmax[64] < 20.0 and wmax[32] > 2 * wmax[64], wmax

@@ -113,6 +113,7 @@ static int plan_stats(vjf_handle* h, StepParams& p) {
     p.s_red = take(VJF_NWARP * VJF_NSCAL + 64);
     size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
     if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
+    if (p.rls64) b2 = std::max(b2, vjf_rls64_floats(p));
     p.s_total = (int)std::max(std::max(off, b2), (size_t)1024);
     if ((size_t)p.s_total * 4 > h->smem_limit) { vjf_set_error("n_rbf=%d too large for this build", p.R); return -1; }
   }

@@ -74,6 +74,8 @@ struct StepParams {
   int use_umma;  // layer-1 weight gradient on tcgen05 (umma.cuh): overlapped schedule, one hidden layer of <= 64 units
   int umma_nk;   // roundup(K1, 8): the N extent of that MMA
   int ldm;  // row stride of the factorisation workspace in phase B2
+  int rls64;    // RLS in double precision (long runs): w_precision shadowed in P64, sweep in double
+  double* P64;  // [R][R]
   // ---- pointers ----
   float* state;
   float* partials;      // [nslots][PS]
@@ -317,9 +319,13 @@ struct vjf_handle {
   cudaEvent_t ev_copied[2], ev_done[2];
   int aux_attr_set;          // aux.cu kernels' shared-memory attribute set on this handle's device
   float* fc_w; size_t fc_w_sz;  // forecast: sampled weights of every step (grow-only)
+  double* P64;                   // double shadow of w_precision (vjf_set_rls_precision)
+  double* wk_ws; size_t wk_ws_sz;  // weight-space Kalman update: fp64 R x R workspace (grow-only)
   float* w1k; float* uk;         // operand images of the tile pipeline
 };
 
+// floats of shared memory the double-precision RLS (rls_factor_f64) needs: [(2R+d)][ldm] + [R] doubles
+static inline size_t vjf_rls64_floats(const StepParams& p) { return 2 * ((size_t)(2 * p.R + p.d) * p.ldm + 2 * p.R + 4) + 2 * VJF_NWARP + 16; }
 void vjf_set_error(const char* fmt, ...);
 extern long long g_vjf_launches;
 #define VJF_CUDA_OK(expr)                                                                         \

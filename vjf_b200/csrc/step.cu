@@ -135,6 +135,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   // [(2R+d)][ldm] + pivots; phase B1: 512 floats
   size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
+  if (p.rls64) b2 = std::max(b2, vjf_rls64_floats(p));
   p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
   return (size_t)p.s_total;
 }
@@ -254,6 +255,9 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
   p.partials = h->partials; p.reduced = h->reduced;
   p.barrier = h->sync_words; p.status = h->sync_words + 16; p.ctrl = h->sync_words + 32;
+  VJF_CUDA_OK(cudaMalloc(&h->P64, (size_t)p.R * p.R * sizeof(double)));
+  VJF_CUDA_OK(cudaMemset(h->P64, 0, (size_t)p.R * p.R * sizeof(double)));
+  p.P64 = h->P64;
   if (vjf_tile_create(h)) return -2;
   *out = h;
   return 0;
@@ -269,7 +273,7 @@ extern "C" int vjf_destroy(vjf_handle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
-  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w);
+  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w); cudaFree(h->wk_ws); cudaFree(h->P64);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   free(h);
@@ -426,6 +430,18 @@ int vjf_internal_reduce(const StepParams& p, cudaStream_t s) {
   vjf_reduce_kernel<<<(p.PS - p.red_begin + 127) / 128, VJF_NT, (size_t)(p.s_b1 + 2048 + 8) * sizeof(float), s>>>(p);
   ++g_vjf_launches;
   VJF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vjf_set_rls_precision(vjf_handle* h, int32_t bits) {
+  if (!h || (bits != 32 && bits != 64)) { vjf_set_error("vjf_set_rls_precision: bits must be 32 or 64"); return -1; }
+  StepParams probe = h->base;
+  probe.rls64 = 1;
+  if (bits == 64 && (vjf_rls64_floats(probe) + 2048 + 64) * sizeof(float) > h->smem_limit) {
+    vjf_set_error("n_rbf=%d: the double-precision factorisation workspace does not fit in shared memory", h->base.R);
+    return -1;
+  }
+  h->base.rls64 = bits == 64;
   return 0;
 }
 

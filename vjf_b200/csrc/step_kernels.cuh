@@ -1254,6 +1254,109 @@ static __device__ bool rls_factor_smem(const StepParams& p, float* sm, float iv,
   return true;
 }
 
+// Double-precision RLS for long runs (vjf_set_rls_precision(h, 64)).  The information-form recursion accumulates phi^T phi / v
+// without forgetting (shrink = 1, vjf/model.py:371): after ~1e7 samples fp32 can neither absorb a step's increment into
+// w_precision nor factorise it (the reference's fp32 run breaks the same way; its float64 configuration, script/example.py:12,
+// does not).  Here w_precision lives in a double shadow `p.P64` (re-seeded from the fp32 state whenever the two disagree, i.e.
+// after the caller loaded a state), the sweep of the augmented matrix [P'; g^T; I] runs in double in shared memory, and the
+// fp32 state receives the rounded results.
+static __device__ bool rls_factor_f64(const StepParams& p, float* smf, float ivf, const float* A, const float* bv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = p.R, d = p.d, ldm = p.ldm;
+  float* st = p.state;
+  float* Pst = st + p.lay.w_precision;
+  const float* Wold = st + p.lay.w_mean;
+  double* P64 = p.P64;
+  double* M = reinterpret_cast<double*>(smf);      // [(2R+d)][ldm]
+  double* dvec = M + (size_t)(2 * R + d) * ldm;    // [R] pivots
+  const double iv = (double)ivf;
+  int mism = 0;
+  for (int i = tid; i < R * R; i += VJF_NT) mism |= ((float)P64[i] != Pst[i]);
+  if (__syncthreads_or(mism)) {
+    for (int i = tid; i < R * R; i += VJF_NT) P64[i] = (double)Pst[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    if (c <= r) M[r * ldm + c] = fma((double)A[i], iv, P64[i]);
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int k = i / d, c = i - k * d;
+    double s = 0.0;
+    for (int j = 0; j < R; ++j) s = fma(P64[k * R + j], (double)Wold[j * d + c], s);
+    M[(R + c) * ldm + k] = fma((double)bv[i], iv, s);
+  }
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    M[(R + d + r) * ldm + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  // 1/x from the fp32 reciprocal + two Newton steps in double (relative error ~1e-14; a double division is ~10x slower and
+  // sits on the serial chain of the sweep)
+  auto recip = [](double x) { double r = (double)__frcp_rn((float)x); r = fma(r, fma(-x, r, 1.0), r); return fma(r, fma(-x, r, 1.0), r); };
+  double piv = M[0];
+  bool fail = !(piv > 0.0 && piv < 1e37);
+  double inv = recip(piv);
+  for (int k = 0; k < R && !fail; ++k) {
+    if (tid == 0) dvec[k] = piv;
+    double pivn = 1.0;
+    if (k + 1 < R) {
+      const double l = M[(k + 1) * ldm + k];
+      pivn = fma(-(l * inv), l, M[(k + 1) * ldm + k + 1]);
+    }
+    const int rend = R + d + k + 1;
+    for (int r = k + 1 + warp; r < rend; r += VJF_NWARP) {
+      const double tk = M[r * ldm + k] * inv;
+      const int jend = (r < R) ? (r + 1) : R;
+      for (int j = k + 1 + lane; j < jend; j += 32) {
+        if (r == k + 1 && j == k + 1) continue;  // next pivot lives in registers
+        M[r * ldm + j] = fma(-tk, M[j * ldm + k], M[r * ldm + j]);
+      }
+    }
+    if (k + 1 < R && !(pivn > 0.0 && pivn < 1e37)) fail = true;
+    piv = pivn;
+    inv = recip(pivn);
+    __syncthreads();
+  }
+  if (fail) return false;
+  __syncthreads();
+  float* Lout = st + p.lay.w_pchol;
+  float* Uout = st + p.lay.w_chol;
+  double* isdv = dvec + R;  // [R] 1/sqrt(pivot)
+  for (int c = tid; c < R; c += VJF_NT) { const double sd = sqrt(dvec[c]); dvec[c] = sd; isdv[c] = 1.0 / sd; }
+  __syncthreads();
+  for (int i = tid; i < R * R; i += VJF_NT) {
+    const int r = i / R, c = i - r * R;
+    const double sd = dvec[c], isd = isdv[c];
+    Lout[i] = (float)((c < r) ? M[r * ldm + c] * isd : ((c == r) ? sd : 0.0));
+    const double uv = (c >= r) ? M[(R + d + r) * ldm + c] * isd : 0.0;
+    M[(R + d + r) * ldm + c] = uv;  // each element is read and written by this thread only
+    Uout[i] = (float)uv;
+    if (p.use_tma) p.u_mirror[r * p.ldu + c] = (float)uv;
+    if (p.tp.on) uk_store(p, c, r, (float)uv);
+    const int lo = (c <= r) ? i : (c * R + r);
+    const double pn = fma((double)A[lo], iv, P64[lo]);
+    M[r * ldm + c] = pn;   // P' (full, symmetric) parked in the dead P rows until every thread has read the old P64
+    Pst[i] = (float)pn;
+  }
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int k = i / d, c = i - k * d;
+    M[(R + c) * ldm + k] = M[(R + c) * ldm + k] * isdv[k];
+  }
+  __syncthreads();
+  for (int i = tid; i < R * R; i += VJF_NT) { const int r = i / R, c = i - r * R; P64[i] = M[r * ldm + c]; }
+  float* Wout = st + p.lay.w_mean;
+  for (int i = tid; i < R * d; i += VJF_NT) {
+    const int r = i / d, c = i - r * d;
+    double s = 0.0;
+    for (int k = r; k < R; ++k) s = fma(M[(R + d + r) * ldm + k], M[(R + c) * ldm + k], s);
+    Wout[i] = (float)s;
+    if (p.tp.on) uk_store(p, p.tp.Rk + c, r, (float)s);
+  }
+  __syncthreads();
+  return true;
+}
+
 // finmask: bit0 recon finite, bit1 dyn finite, bit2 entropy finite (from the reduced sums)
 static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned finmask, const unsigned* wait_ctr = nullptr,
                                 unsigned wait_val = 0) {
@@ -1272,7 +1375,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   // Overlapped Poisson schedule: the caller hands over the statistics-ready counter instead of waiting itself.  When the
   // register factorisation runs, its statistics-independent part (old P, P W) is done first and the wait happens inside
   // it; the loss sums (one thread, nothing waits for them) are then written after the factorisation.
-  const bool defer = wait_ctr && upd && !warm && p.R <= 128 && !p.init_mode && p.lik == VJF_LIK_POISSON;
+  const bool defer = wait_ctr && upd && !warm && p.R <= 128 && !p.init_mode && p.lik == VJF_LIK_POISSON && !p.rls64;
   if (wait_ctr && !defer) wait_counter(wait_ctr, wait_val);
   auto losses_and_likelihood = [&](int who) {
     if (p.world > 1) finmask = (isfinite(scal[SC_RECON]) ? 1u : 0u) | (isfinite(scal[SC_DYN]) ? 2u : 0u) | (isfinite(scal[SC_ENT]) ? 4u : 0u);
@@ -1322,7 +1425,8 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     const int nr8 = (2 * R + d + 7) / 8;  // rows per warp with 8 sweep warps
     (void)nr16;
     (void)nr8;
-    if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    if (p.rls64) ok = rls_factor_f64(p, sm, iv, A, bv);
+    else if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
     else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
     else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
     else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }

@@ -169,6 +169,7 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   if (flush_floats * 4 > pl.scratch_bytes) return 0;
   size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) return 0;
+  if (p.rls64) b2 = std::max(b2, vjf_rls64_floats(p));
   const int s_b1 = (int)((b2 + 3) & ~(size_t)3);
   if ((size_t)(s_b1 + 2048 + 8) * 4 > (size_t)(pl.o_uk - pl.o_pg)) return 0;
   // observations as a 3-D tensor [T][B][D]: boxes of {32 columns, TBR trials, 1 step}, 16-byte pieces swizzled within

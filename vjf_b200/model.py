@@ -68,7 +68,8 @@ class _Optimizer:
 
 class VJF(nn.Module):
     def __init__(self, ydim: int, xdim: int, udim: int, n_rbf: int, hidden_sizes: Sequence[int], likelihood: str = "poisson",
-                 *, lr: float = 1e-4, lr_decay: float = .9, device=None, max_trials: int = 65536, seed: int = 0):
+                 *, lr: float = 1e-4, lr_decay: float = .9, device=None, max_trials: int = 65536, seed: int = 0,
+                 rls_precision: int = 32):
         """Use VJF.make_model (same advice as the reference, vjf/model.py:53-54)."""
         super().__init__()
         if not torch.cuda.is_available():
@@ -92,6 +93,8 @@ class VJF(nn.Module):
             _lib.check(self._lib.vjf_create(C.byref(self._cfg), _ptr(self._flat), C.byref(h)))
             self._h = h
             _lib.check(self._lib.vjf_init_state(self._h, self._stream()))
+            if int(rls_precision) != 32:  # 64: double-precision RLS for long horizons (what the reference gets from float64)
+                _lib.check(self._lib.vjf_set_rls_precision(self._h, int(rls_precision)))
         self._loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._build_modules()
         self._init_random()
