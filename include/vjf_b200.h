@@ -172,6 +172,13 @@ int vjf_run_sharded_host(vjf_handle* h, int32_t T, int32_t B_local, int32_t B_gl
  * samples and its Cholesky fails after ~1e7 samples (VJF_ST_CHOL_FAILED).  Needed for long horizons (T = 100 000). */
 int vjf_set_rls_precision(vjf_handle* h, int32_t bits);
 
+/* n_rbf > 160 (BASELINE config 3, n_rbf = 1024) runs a different schedule under the same entry points (vjf_step / vjf_run /
+ * vjf_run_host): per time step a short sequence of launches with phi w_chol and phi^T phi as tcgen05 GEMMs over all trials and a
+ * blocked multi-CTA Cholesky (csrc/bigr.cu); vjf_last_launch_kind() reports 2.  Not available there: the sharded run,
+ * vjf_rls_initialize, vjf_weight_kalman, the double-precision RLS.  vjf_bigr_buffer returns device views of its workspace for tests
+ * and profiling: 0 phi [B][n_rbf], 1 p_mean [B][xdim], 2 p_logvar [B], 3 split-K partial sums of phi^T phi; NULL otherwise. */
+float* vjf_bigr_buffer(vjf_handle* h, int32_t which);
+
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);
 

@@ -8,6 +8,7 @@
 
 #define VJF_NT 512               // threads per CTA of the step kernels
 #define VJF_NWARP (VJF_NT / 32)
+#define VJF_BIGR_MIN 160           // n_rbf above this runs the large-n_rbf path (bigr.cu)
 #define VJF_TB_MAX 32            // trials per tile (rows of the per-CTA tile)
 #define VJF_NSCAL 8              // scalar sums carried in the partial vector
 #define TK_NCW 15                // compute warps of the tile pipeline (warp 15 is its control warp)
@@ -74,6 +75,8 @@ struct StepParams {
   int use_umma;  // layer-1 weight gradient on tcgen05 (umma.cuh): overlapped schedule, one hidden layer of <= 64 units
   int umma_nk;   // roundup(K1, 8): the N extent of that MMA
   int ldm;  // row stride of the factorisation workspace in phase B2
+  // large n_rbf (> 128, bigr.cu): RBF features, dynamics read-out and RLS statistics live outside the tile kernels
+  int ext; const float* ext_xs; const float* ext_pm; const float* ext_plv; float* ext_dx;
   int rls64;    // RLS in double precision (long runs): w_precision shadowed in P64, sweep in double
   double* P64;  // [R][R]
   // ---- pointers ----
@@ -320,6 +323,7 @@ struct vjf_handle {
   int aux_attr_set;          // aux.cu kernels' shared-memory attribute set on this handle's device
   float* fc_w; size_t fc_w_sz;  // forecast: sampled weights of every step (grow-only)
   double* P64;                   // double shadow of w_precision (vjf_set_rls_precision)
+  struct BigR* bigr;             // workspace of the large-n_rbf path (bigr.cu)
   double* wk_ws; size_t wk_ws_sz;  // weight-space Kalman update: fp64 R x R workspace (grow-only)
   float* w1k; float* uk;         // operand images of the tile pipeline
 };

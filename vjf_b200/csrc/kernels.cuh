@@ -14,3 +14,10 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_tile_kernel(const __grid_consta
 int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int T, int B, CUtensorMap* map, cudaStream_t stream);
 int vjf_tile_launch(vjf_handle* h, StepParams& p, const CUtensorMap& map, cudaStream_t s);
 int vjf_tile_create(vjf_handle* h);
+
+// large n_rbf (bigr.cu): per-step launch sequence with the RBF contractions as tcgen05 GEMMs and a blocked multi-CTA factorisation
+int vjf_bigr_create(vjf_handle* h);
+void vjf_bigr_destroy(vjf_handle* h);
+int vjf_bigr_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s);
+int vjf_plan_tiles_public(vjf_handle* h, StepParams& p, int B);
+int vjf_internal_reduce(const StepParams& p, cudaStream_t s);

@@ -101,8 +101,9 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.in_split = in_split ? 1 : 0;
   p.s_inl = in_split ? take((size_t)rows * p.K1p) : p.s_in;
   p.s_g = take((size_t)((tb + 3) & ~3) * p.Dp);  // only real trials are read back
-  p.s_phi = take((size_t)rows * p.Rp);
-  p.s_phil = take((size_t)rows * p.Rp);
+  const bool ext = p.ext != 0;  // large n_rbf (bigr.cu): nothing of size n_rbf lives in the tile kernels' shared memory
+  p.s_phi = take(ext ? 0 : (size_t)rows * p.Rp);
+  p.s_phil = take(ext ? 0 : (size_t)rows * p.Rp);
   for (int l = 0; l < p.L; ++l) p.s_act[l] = take((size_t)rows * p.Hp[l]);
   p.s_gpa = take((size_t)rows * p.Gp);
   p.s_gpal = take((size_t)rows * p.Gp);
@@ -114,7 +115,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_xt = take((size_t)rows * p.d); p.s_mt = take((size_t)rows * p.d); p.s_lt = take((size_t)rows * p.d);
   p.s_pm = take((size_t)rows * p.d); p.s_dx = take((size_t)rows * p.d); p.s_gxt = take((size_t)rows * p.d);
   p.s_gmt = take((size_t)rows * p.d); p.s_glt = take((size_t)rows * p.d); p.s_plv = take((size_t)rows);
-  p.s_qp = take((size_t)((p.R + 7) / 8) * 32 + 32);
+  p.s_qp = take(ext ? 32 : (size_t)((p.R + 7) / 8) * 32 + 32);
   p.U_in_smem = u_in_smem ? 1 : 0;
   p.s_U = take(u_in_smem ? (size_t)((p.R + 7) & ~7) * p.ldu : 0);
   p.dec_in_smem = dec_in_smem ? 1 : 0;
@@ -126,9 +127,9 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   p.s_flag = take(12);  // [0] flag, [1] TMEM base, [2..7] three mbarriers, [8] non-finite partial seen, [9] barrier broadcast
   p.s_scf = take(VJF_NSCAL);
   p.s_b1 = take(2048 + 8);
-  p.s_W = take((size_t)p.R * p.d);
-  p.s_c = take((size_t)p.R * p.du);
-  p.s_iw = take((size_t)p.R);
+  p.s_W = take(ext ? 0 : (size_t)p.R * p.d);
+  p.s_c = take(ext ? 0 : (size_t)p.R * p.du);
+  p.s_iw = take(ext ? 0 : (size_t)p.R);
   p.s_red = take((size_t)VJF_NWARP * VJF_NSCAL + 64);
   const size_t a = off;
   // phase B2: register path needs ~2(2R+d) + R + 2dR floats; the shared-memory fallback (R > 128)
@@ -136,6 +137,7 @@ static size_t plan_smem(StepParams& p, int tb, bool u_in_smem, bool dec_in_smem,
   size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) b2 = (size_t)(2 * p.R + p.d) * p.ldm + ((p.R + 3) & ~3) + 4 + 2 * VJF_NWARP + 8;
   if (p.rls64) b2 = std::max(b2, vjf_rls64_floats(p));
+  if (ext) b2 = 1024;
   p.s_total = (int)std::max(std::max(a, b2), (size_t)1024);
   return (size_t)p.s_total;
 }
@@ -148,7 +150,7 @@ static int plan_tiles(vjf_handle* h, StepParams& p, int B, int max_slots, int pe
   if (persistent && max_slots > 1 && (B + VJF_TB_MAX - 1) / VJF_TB_MAX <= max_slots - 1) { p.overlap = 1; max_slots -= 1; }
   const int want = std::min(std::max((int)up((B + max_slots - 1) / max_slots, 4), 4), VJF_TB_MAX);
   const size_t limit = h->smem_limit;
-  bool u_smem = (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
+  bool u_smem = !p.ext && (size_t)((p.R + 7) & ~7) * p.ldu * 4 <= 96 * 1024;
   bool dec_smem = (size_t)(p.d + 1) * p.D * 4 <= 32 * 1024;
   bool w1_smem = (size_t)p.K1 * p.ldw1 * 4 <= 72 * 1024;
   bool in_split = true;
@@ -236,8 +238,9 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   lay_to_int(lay, p.lay);
   p.G = p.lay.n_train;
   p.pa = p.G;
-  p.pb = (int)up(p.pa + (int64_t)p.R * p.R, 4);
-  p.ps = (int)up(p.pb + (int64_t)p.R * p.d, 4);
+  p.ext = p.R > VJF_BIGR_MIN ? 1 : 0;  // large n_rbf: the RLS statistics are GEMM outputs (bigr.cu), not slot sums
+  p.pb = p.ext ? p.pa : (int)up(p.pa + (int64_t)p.R * p.R, 4);
+  p.ps = p.ext ? p.pb : (int)up(p.pb + (int64_t)p.R * p.d, 4);
   p.PS = p.ps + VJF_NSCAL;
   p.ldm = (p.R + 1) | 1;
   p.state = state;
@@ -246,7 +249,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaMalloc(&h->partials, part_bytes));
   VJF_CUDA_OK(cudaMemset(h->partials, 0, part_bytes));
   // reduced vector, followed by the row-padded mirror of the recognition layer-1 weight (TMA source, 128-byte aligned)
-  const size_t red_floats = (size_t)up(p.PS, 32) + (size_t)up((int64_t)p.K1 * p.ldw1, 32) + (size_t)((p.R + 7) & ~7) * p.ldu;
+  const size_t red_floats = (size_t)up(p.PS, 32) + (size_t)up((int64_t)p.K1 * p.ldw1, 32) + (p.ext ? 32 : (size_t)((p.R + 7) & ~7) * p.ldu);
   VJF_CUDA_OK(cudaMalloc(&h->reduced, red_floats * sizeof(float)));
   VJF_CUDA_OK(cudaMemset(h->reduced, 0, red_floats * sizeof(float)));
   p.w1_mirror = h->reduced + up(p.PS, 32);
@@ -255,10 +258,13 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   VJF_CUDA_OK(cudaMemset(h->sync_words, 0, 64 * sizeof(unsigned)));
   p.partials = h->partials; p.reduced = h->reduced;
   p.barrier = h->sync_words; p.status = h->sync_words + 16; p.ctrl = h->sync_words + 32;
-  VJF_CUDA_OK(cudaMalloc(&h->P64, (size_t)p.R * p.R * sizeof(double)));
-  VJF_CUDA_OK(cudaMemset(h->P64, 0, (size_t)p.R * p.R * sizeof(double)));
-  p.P64 = h->P64;
+  if (!p.ext) {
+    VJF_CUDA_OK(cudaMalloc(&h->P64, (size_t)p.R * p.R * sizeof(double)));
+    VJF_CUDA_OK(cudaMemset(h->P64, 0, (size_t)p.R * p.R * sizeof(double)));
+    p.P64 = h->P64;
+  }
   if (vjf_tile_create(h)) return -2;
+  if (p.ext && vjf_bigr_create(h)) return -2;
   *out = h;
   return 0;
 }
@@ -273,7 +279,7 @@ extern "C" int vjf_destroy(vjf_handle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
-  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w); cudaFree(h->wk_ws); cudaFree(h->P64);
+  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w); cudaFree(h->wk_ws); cudaFree(h->P64); vjf_bigr_destroy(h);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   free(h);
@@ -329,6 +335,11 @@ static int check_ptrs(const vjf_handle* h, const void* y, const float* u, const 
 
 // the throughput tile pipeline when the shapes are in its plan, else the persistent kernel of k_persistent.cu
 static int launch_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s) {
+  if (p.ext) {
+    if (p.world > 1) { vjf_set_error("n_rbf > %d: the sharded run is not implemented for the large-n_rbf path", VJF_BIGR_MIN); return -1; }
+    g_vjf_last_kind = 2;
+    return vjf_bigr_time_loop(h, p, T, B, s);
+  }
   CUtensorMap map;
   const int use_tile = vjf_tile_plan(h, p, p.y, p.y_dtype, T, B, &map, s);
   if (use_tile < 0) return -2;
@@ -426,6 +437,8 @@ extern "C" int vjf_step(vjf_handle* h, int32_t B, const float* y, const float* u
                  out_loss, stream);
 }
 
+int vjf_plan_tiles_public(vjf_handle* h, StepParams& p, int B) { return plan_tiles(h, p, B, h->max_slots); }
+
 int vjf_internal_reduce(const StepParams& p, cudaStream_t s) {
   vjf_reduce_kernel<<<(p.PS - p.red_begin + 127) / 128, VJF_NT, (size_t)(p.s_b1 + 2048 + 8) * sizeof(float), s>>>(p);
   ++g_vjf_launches;
@@ -435,6 +448,7 @@ int vjf_internal_reduce(const StepParams& p, cudaStream_t s) {
 
 extern "C" int vjf_set_rls_precision(vjf_handle* h, int32_t bits) {
   if (!h || (bits != 32 && bits != 64)) { vjf_set_error("vjf_set_rls_precision: bits must be 32 or 64"); return -1; }
+  if (h->base.ext && bits == 64) { vjf_set_error("n_rbf > %d: the large-n_rbf path factorises in fp32", VJF_BIGR_MIN); return -1; }
   StepParams probe = h->base;
   probe.rls64 = 1;
   if (bits == 64 && (vjf_rls64_floats(probe) + 2048 + 64) * sizeof(float) > h->smem_limit) {

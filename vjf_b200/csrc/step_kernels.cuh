@@ -274,7 +274,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
         } else {
           // pad rows of everything that is summed over the rows of the tile
           for (int j = lane; j < K1p; j += 32) dst[j] = 0.f;
-          for (int j = lane; j < Rp; j += 32) { phi_s[b * Rp + j] = 0.f; phil_s[b * Rp + j] = 0.f; }
+          if (!p.ext) for (int j = lane; j < Rp; j += 32) { phi_s[b * Rp + j] = 0.f; phil_s[b * Rp + j] = 0.f; }
           for (int j = lane; j < Gp; j += 32) { gpa[b * Gp + j] = 0.f; gpb[b * Gp + j] = 0.f; gpal[b * Gp + j] = 0.f; gpbl[b * Gp + j] = 0.f; }
           for (int j = lane; j < d; j += 32) { dx_s[b * d + j] = 0.f; gmt_s[b * d + j] = 0.f; glt_s[b * d + j] = 0.f; xt_s[b * d + j] = 0.f; }
         }
@@ -285,7 +285,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     __syncthreads();
 
     VJF_STAMP(p, t, 8);
-    if (first && !(tma && cx->consts_staged)) {  // finish the staged RBF widths: -1/(2 w^2)
+    if (first && !p.ext && !(tma && cx->consts_staged)) {  // finish the staged RBF widths: -1/(2 w^2)
       for (int i = tid; i < R; i += VJF_NT) { const float w = expf(iw_s[i]); iw_s[i] = -0.5f / (w * w); }
     }
     if (tma) cx->consts_staged = 1;
@@ -293,7 +293,8 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     for (int i = tid; i < nb * du; i += VJF_NT) {
       const int b = i / du, k = i - b * du;
       float v;
-      if (k < d) v = in_s[b * K1p + D + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * in_s[b * K1p + D + u + d + k]);
+      if (k < d) v = p.ext ? p.ext_xs[(size_t)(b0 + b) * d + k]  // large n_rbf (bigr.cu): drawn by the feature kernel
+                           : in_s[b * K1p + D + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * in_s[b * K1p + D + u + d + k]);
       else v = in_s[b * K1p + D + (k - d)];
       xu_s[b * du + k] = v;
     }
@@ -302,7 +303,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     VJF_STAMP(p, t, 9);
     // ---- S2: RBF features phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22), stored as a (hi, lo) pair;
     //      the staged input matrix is split in place the same way (its extras were consumed by S1) ----
-    for (int b = warp; b < nb; b += VJF_NWARP) {
+    for (int b = warp; b < nb && !p.ext; b += VJF_NWARP) {
       for (int k = lane; k < Rp; k += 32) {
         float v = 0.f;
         if (k < R) {
@@ -419,6 +420,9 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
       *reinterpret_cast<int*>(sm + p.s_flag + 10) = 1;
     }
     // ---- S9: RLS sufficient statistics (vjf/module.py:94-96, unscaled): A += phi^T phi, b += phi^T dx ----
+    if (p.ext) {  // large n_rbf: the statistics are two GEMMs over all trials (bigr.cu); hand over dx = xt - xs
+      for (int i = tid; i < nb * d; i += VJF_NT) p.ext_dx[(size_t)b0 * d + i] = dx_s[i];
+    } else {
     mma_gram(phi_s, phil_s, Rp, R, rows, slot + p.pa, first);
     {
       float* bp = slot + p.pb;
@@ -428,6 +432,7 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
         for (int b = 0; b < nb; ++b) s = fmaf(phi_s[b * Rp + r] + phil_s[b * Rp + r], dx_s[b * d + k], s);
         acc_store(bp + i, s, first);
       }
+    }
     }
     VJF_STAMP(p, t, 19);
     if (part == PART_FRONT) {
@@ -472,7 +477,9 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   }
   // ---- S3: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W ;
   //      p_logvar = log |phi w_chol|^2  (the diagonal of the reference's (B,B) product) ----
-  if (p.U_in_smem) {
+  if (p.ext) {
+    // large n_rbf: p_mean and p_logvar come from the feature kernel and the phi w_chol GEMM
+  } else if (p.U_in_smem) {
     mma_quadform(phi_s, phil_s, Rp, sm + p.s_U, p.ldu, R, rows, qp_s, *flag_s == 0);
   } else {
     const float* U = st + p.lay.w_chol;
@@ -490,6 +497,9 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
     }
   }
   VJF_STAMP(p, t, 49);
+  if (p.ext) {
+    for (int i = tid; i < nb * d; i += VJF_NT) pm_s[i] = p.ext_pm[(size_t)b0 * d + i];
+  } else
   for (int i = tid; i < nb * d; i += VJF_NT) {  // one thread per (trial, state dim): four independent chains of length R/4
     const int b = i / d, k = i - b * d;
     const float* ph = phi_s + b * Rp;
@@ -510,9 +520,12 @@ static __device__ __forceinline__ void phase_a_tile(const StepParams& p, float* 
   VJF_STAMP(p, t, 51);
   // p_logvar from the n-tile partial sums
   if (tid < nb) {
+    if (p.ext) plv_s[tid] = p.ext_plv[b0 + tid];
+    else {
     float q = qp_s[tid];
     if (p.U_in_smem) { const int nt = (R + 7) >> 3; for (int n = 1; n < nt; ++n) q += qp_s[n * rows + tid]; }
     plv_s[tid] = logf(q);
+    }
   }
   __syncthreads();
 
@@ -681,7 +694,7 @@ static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what
   if (what & STAGE_FRONT) {
     // RBF centres and widths are not trained (vjf/module.py:115-130: requires_grad=False) and the RLS does not touch
     // them: with a dedicated tile per CTA they are staged once per launch
-    if (!tma || !cx->consts_staged) {
+    if (!p.ext && (!tma || !cx->consts_staged)) {
       stage_async(sm + p.s_c, p.du, st + p.lay.centroid, p.du, p.R, p.du, tid, VJF_NT);
       stage_async(sm + p.s_iw, p.R, st + p.lay.logwidth, p.R, 1, p.R, tid, VJF_NT);
     }
@@ -728,7 +741,7 @@ static __device__ void phase_a_prologue(const StepParams& p, float* sm, int what
     // w_chol from its row-padded mirror (kept current by the RLS commit; pads are zero) and w_mean: two TMA bulk copies,
     // completion on the mbarrier the back half waits on
     if (tid == 0) issue_back_tma(p, sm);
-  } else if (what & STAGE_BACK) {
+  } else if ((what & STAGE_BACK) && !p.ext) {
     stage_async(sm + p.s_W, p.d, st + p.lay.w_mean, p.d, p.R, p.d, tid, VJF_NT);
     if (p.U_in_smem) {
       float* U_s = sm + p.s_U;
@@ -1408,6 +1421,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   };
   if (!defer) losses_and_likelihood(0);
   VJF_STAMP(p, t, 24);
+  if (p.ext) return;  // large n_rbf: the RLS and the state-noise update run as their own kernels (bigr.cu)
   if (!upd) {
     if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
     return;
