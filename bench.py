@@ -35,6 +35,9 @@ C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[
 # BASELINE.json configs[3]: neural-population scale, 65536 trials sharded over the GPUs (strong scaling), SURVEY.md 8d row C4
 C4 = dict(name="C4-population-poisson", ydim=2000, xdim=8, udim=0, n_rbf=64, hidden=[128], likelihood="poisson",
           global_trials=65536, T=8)
+# BASELINE.json configs[2]: the tensor-pipe configuration: 1024 RBFs, 16 384 trials, Gaussian observations
+C3 = dict(name="C3-rbf1024-gaussian", ydim=500, xdim=10, udim=0, n_rbf=1024, hidden=[128], likelihood="gaussian",
+          trials_per_gpu=16384, T=16)
 # BASELINE.json configs[4]: long-horizon latency path: 1024 trials, T = 100 000, Gaussian observations
 C5 = dict(name="C5-long-horizon-gaussian", ydim=50, xdim=4, udim=0, n_rbf=32, hidden=[32], likelihood="gaussian",
           trials_per_gpu=1024, T=100000)
@@ -355,6 +358,37 @@ def limit_cycle_gaussian(t0, T, B, D, dev, seed):
     return x @ Cm + b + 0.1 * torch.randn(T, B, D, device=dev, generator=gn)
 
 
+def rotation_gaussian(T, B, D, d, dev, seed):
+    """latent = stable random rotation (pairs of planes, radius pulled towards 1) + 0.1 noise, roughly
+    unit variance; y = x C + b + 0.1 N(0,1).  Generated on the device."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    th = torch.rand(d // 2, device=dev, generator=g) * 0.3 + 0.05
+    x = torch.randn(B, d, device=dev, generator=g)
+    Cm = torch.randn(d, D, device=dev, generator=g) / d ** 0.5
+    b = torch.randn(D, device=dev, generator=g) * 0.5
+    y = torch.empty(T, B, D, device=dev)
+    c, s_ = torch.cos(th), torch.sin(th)
+    for t in range(T):
+        xe, xo = x[:, 0::2].clone(), x[:, 1::2].clone()
+        x[:, 0::2] = c * xe - s_ * xo
+        x[:, 1::2] = s_ * xe + c * xo
+        r = x.pow(2).mean(-1, keepdim=True).sqrt()
+        x = x * (1 + 0.1 * (1 - r)) + 0.1 * torch.randn(B, d, device=dev, generator=g)
+        y[t] = x @ Cm + b + 0.1 * torch.randn(B, D, device=dev, generator=g)
+    return y
+
+
+def c3_tensor_flops_per_step(B, R):
+    """tcgen05 FLOPs the large-n_rbf path issues per time step: GEMM 1 (phi w_chol, the K chunks past a tile's last column
+    skipped: 5/8 of B R^2 MACs at n_rbf = 1024) and GEMM 2 (phi^T phi, 20 of 32 tiles), three tf32 products per MAC."""
+    nt = (R + 255) // 256
+    k1 = sum(min(R, 256 * (j + 1)) for j in range(nt)) * 256           # K columns x N columns summed over the N tiles
+    mt = (R + 127) // 128
+    t2 = sum(1 for i in range(mt) for j in range(nt) if i >= 2 * j)
+    return 3 * 2 * (B * k1 + t2 * 128 * 256 * B)
+
+
 def time_runs(fn, reps):
     """Mean CUDA-event time (ms) of fn() over reps calls, after one warm-up call."""
     import torch
@@ -633,6 +667,33 @@ def run_ours(args, cfg):
                 "value": B5 * T5 / (ms5 * 1e-3), "unit": "trial-steps/s", "status_word": st5, "final_loss": float(ls5[:, 0].mean().item()),
                 "kernel_kind": int(lib.vjf_last_launch_kind()), "note": "latency-bound path (SURVEY 8d): report us/step"}
             del m5
+    if world == 1 and not args.no_extras:
+        # (d) C3, the tensor-pipe configuration: n_rbf = 1024, 16 384 trials -- the large-n_rbf launch sequence (csrc/bigr.cu)
+        c3 = C3
+        B3, T3 = c3["trials_per_gpu"], c3["T"]
+        m3 = VJF.make_model(c3["ydim"], c3["xdim"], 0, c3["n_rbf"], c3["hidden"], c3["likelihood"], max_trials=B3, seed=99, device=dev)
+        m3.load_full_state(bench_state(c3))
+        y3 = rotation_gaussian(T3, B3, c3["ydim"], c3["xdim"], dev, 17)
+        st3 = m3._flat.clone()
+
+        def step_3():
+            m3._flat.copy_(st3)
+            m3.run(y3)
+        ms = time_runs(step_3, 3)
+        tps = B3 * T3 / (ms * 1e-3)
+        fl = c3_tensor_flops_per_step(B3, c3["n_rbf"])
+        extras["c3_tensor_pipe"] = {
+            "workload": f"{c3['name']}: xdim 10 ydim 500 gaussian n_rbf 1024 hidden [128], {B3} trials x {T3} time steps, in-kernel Philox",
+            "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T3 * 1e3, "kernel_kind": int(lib.vjf_last_launch_kind()),
+            "status_word": int(m3.status()),
+            "tensor_pipe": {"tensor_flops_per_time_step": fl, "achieved_tflops": fl / (ms / T3 * 1e-3) / 1e12, "peak_tflops": tf32_peak,
+                            "frac": fl / (ms / T3 * 1e-3) / 1e12 / tf32_peak,
+                            "useful_flops_per_time_step": 2 * 2 * B3 * c3["n_rbf"] ** 2 // 2,
+                            "note": "whole-step utilisation (GEMMs + everything else of the step) against MEASURED_PEAKS.json bf16_tflops_sustained / 2; "
+                                    "three tf32 products per multiply-add (hi/lo operand split) for fp32-grade results"},
+            "roofline": {"bound": "tensor", "achieved": fl / (ms / T3 * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": fl / (ms / T3 * 1e-3) / 1e12 / tf32_peak}}
+        del m3, y3
     if world > 1 and not args.no_extras:
         # C4 strong scaling: 65536 trials in all, sharded over the ranks (BASELINE.json configs[3])
         from vjf_b200.distributed import ShardedVJF as _S

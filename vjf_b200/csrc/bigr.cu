@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 #include <cuda.h>
 
@@ -32,10 +33,13 @@
 
 struct BigR {
   int Bmax, Bp, SK, NP;
-  float *phi, *phiT, *xs, *pm, *plv, *dx, *part1, *Ut, *Apart, *bstat, *M, *Pnew;
+  float *phi, *phiT, *xs, *pm, *plv, *dx, *part1, *Ut, *Apart, *bstat, *M, *Pnew;  // bstat: [BSPLIT][R][d] partial sums
   double* rpart;
   unsigned* ctl;  // [0] grid barrier, [1] fail flag
 };
+
+constexpr int BIGR_BSPLIT = 8;   // phi^T dx: the trials are split over this many CTAs per group of 8 RBFs (bytes in flight)
+constexpr int BIGR_FT = 16;      // trials per CTA of the feature kernel
 
 namespace bg {
 constexpr int BM = 128, BN = 256;
@@ -188,17 +192,19 @@ bigr_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // features: xs, phi, phi^T, p_mean  (vjf/util.py:11-13, vjf/functional.py:11-22, vjf/model.py:338)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) bigr_feat_kernel(const StepParams p, const BigR w, int t) {
+__global__ void __launch_bounds__(512) bigr_feat_kernel(const StepParams p, const BigR w, int t) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int FT = BIGR_FT;
   const int tid = threadIdx.x, R = p.R, d = p.d, u = p.u, du = p.du, ldt = R + 1;
-  float* tile = sm;                 // [32][R + 1]
-  float* xu_s = tile + 32 * ldt;    // [32][du]
-  const int b0 = blockIdx.x * 32, nb = min(32, p.B - b0);
+  float* tile = sm;                 // [FT][R + 1]
+  float* xu_s = tile + FT * ldt;    // [FT][du]
+  float* Wt = xu_s + ((FT * du + 3) & ~3);  // [d][R]  w_mean transposed: conflict-free reads with the lanes over the RBFs
+  const int b0 = blockIdx.x * FT, nb = min(FT, p.B - b0);
   const float* st = p.state;
   const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
   const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
   const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-  for (int i = tid; i < 32 * du; i += blockDim.x) {
+  for (int i = tid; i < FT * du; i += blockDim.x) {
     const int b = i / du, k = i - b * du;
     float v = 0.f;
     if (b < nb) {
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(512, 1) bigr_feat_kernel(const StepParams p, c
     }
     xu_s[i] = v;
   }
+  for (int i = tid; i < R * d; i += blockDim.x) { const int r = i / d, k = i - r * d; Wt[k * R + r] = st[p.lay.w_mean + i]; }
   __syncthreads();
   const float* cen = st + p.lay.centroid;
   const float* lw = st + p.lay.logwidth;
@@ -224,7 +231,8 @@ __global__ void __launch_bounds__(512, 1) bigr_feat_kernel(const StepParams p, c
     for (int k = 0; k < du; ++k) c[k] = cen[r * du + k];
     const float wd = expf(lw[r]);
     const float iw = -0.5f / (wd * wd);
-    for (int b = 0; b < 32; ++b) {
+#pragma unroll 4
+    for (int b = 0; b < FT; ++b) {
       float v = 0.f;
       if (b < nb) {
         float d2 = 0.f;
@@ -236,29 +244,26 @@ __global__ void __launch_bounds__(512, 1) bigr_feat_kernel(const StepParams p, c
     }
   }
   __syncthreads();
-  for (int i = tid; i < 32 * R; i += blockDim.x) {
-    const int r = i >> 5, b = i & 31;
+  for (int i = tid; i < FT * R; i += blockDim.x) {
+    const int r = i / FT, b = i % FT;
     if (b0 + b < w.Bp) w.phiT[(size_t)r * w.Bp + b0 + b] = tile[b * ldt + r];
   }
-  // p_mean = xs + phi W: 16 threads per trial, each a strided part of the sum, combined by shuffles
+  // p_mean = xs + phi W: one warp per trial, lanes over the RBFs
   {
-    const int b = tid >> 4, part = tid & 15;
+    const int b = tid >> 5, lane = tid & 31;
     float acc[VJF_MAX_XDIM];
 #pragma unroll
     for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
-    const float* W = st + p.lay.w_mean;
-    for (int r = part; r < R; r += 16) {
+    for (int r = lane; r < R; r += 32) {
       const float ph = tile[b * ldt + r];
 #pragma unroll
       for (int k = 0; k < VJF_MAX_XDIM; ++k)
-        if (k < d) acc[k] = fmaf(ph, W[r * d + k], acc[k]);
+        if (k < d) acc[k] = fmaf(ph, Wt[k * R + r], acc[k]);
     }
 #pragma unroll
     for (int k = 0; k < VJF_MAX_XDIM; ++k) {
-      float s = acc[k];
-      s += __shfl_xor_sync(0xffffffffu, s, 8, 16); s += __shfl_xor_sync(0xffffffffu, s, 4, 16);
-      s += __shfl_xor_sync(0xffffffffu, s, 2, 16); s += __shfl_xor_sync(0xffffffffu, s, 1, 16);
-      if (part == 0 && k < d && b < nb) w.pm[(size_t)(b0 + b) * d + k] = xu_s[b * du + k] + s;
+      const float sum = warp_sum(acc[k]);
+      if (lane == 0 && k < d && b < nb) w.pm[(size_t)(b0 + b) * d + k] = xu_s[b * du + k] + sum;
     }
   }
 }
@@ -287,24 +292,38 @@ __global__ void bigr_transpose_kernel(const float* __restrict__ in, float* __res
   }
 }
 
-// b = phi^T dx (R x d): one warp per RBF, lanes over the trials
+// b = phi^T dx (R x d): one warp per RBF, lanes over the trials; the dx chunk of 256 trials is staged once per CTA
 __global__ void __launch_bounds__(256) bigr_bstat_kernel(const StepParams p, const BigR w) {
+  __shared__ float dxs[256 * VJF_MAX_XDIM];
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, d = p.d;
-  if (r >= p.R) return;
   float acc[VJF_MAX_XDIM];
 #pragma unroll
   for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
-  const float* row = w.phiT + (size_t)r * w.Bp;
-  for (int b = lane; b < p.B; b += 32) {
-    const float ph = row[b];
+  const float* row = w.phiT + (size_t)min(r, p.R - 1) * w.Bp;
+  const int per = (((p.B + BIGR_BSPLIT - 1) / BIGR_BSPLIT) + 255) & ~255;
+  const int cbeg = blockIdx.y * per, cend = min(p.B, cbeg + per);
+  for (int c0 = cbeg; c0 < cend; c0 += 256) {
+    const int nb = min(256, cend - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * d; i += 256) dxs[i] = w.dx[(size_t)c0 * d + i];
+    __syncthreads();
+    float ph[8];
 #pragma unroll
-    for (int k = 0; k < VJF_MAX_XDIM; ++k)
-      if (k < d) acc[k] = fmaf(ph, w.dx[(size_t)b * d + k], acc[k]);
+    for (int i = 0; i < 8; ++i) { const int b = lane + 32 * i; ph[i] = (b < nb) ? row[c0 + b] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int b = lane + 32 * i;
+      if (b < nb) {
+#pragma unroll
+        for (int k = 0; k < VJF_MAX_XDIM; ++k)
+          if (k < d) acc[k] = fmaf(ph[i], dxs[b * d + k], acc[k]);
+      }
+    }
   }
 #pragma unroll
   for (int k = 0; k < VJF_MAX_XDIM; ++k) {
-    const float s = warp_sum(acc[k]);
-    if (lane == 0 && k < d) w.bstat[r * d + k] = s;
+    const float sum = warp_sum(acc[k]);
+    if (lane == 0 && k < d && r < p.R) w.bstat[((size_t)blockIdx.y * p.R + r) * d + k] = sum;
   }
 }
 
@@ -327,14 +346,39 @@ __global__ void bigr_setup_kernel(const StepParams p, const BigR w) {
       w.Pnew[i] = v;
       if (c > r) v = 0.f;
     } else if (r < R + d) {
-      const int k = r - R;
-      float s = 0.f;
-      for (int j = 0; j < R; ++j) s = fmaf(P[(size_t)j * R + c], st[p.lay.w_mean + j * d + k], s);  // P symmetric: column c read along rows
-      v = fmaf(w.bstat[c * d + k], iv, s);
+      continue;  // g^T: bigr_g_kernel
     } else {
       v = (c == r - R - d) ? 1.0f : 0.f;
     }
     w.M[i] = v;
+  }
+}
+
+// g = P W + b / v (old P, old W: vjf/module.py:93) into rows [R, R + d) of the work matrix: one warp per row of P
+__global__ void __launch_bounds__(256) bigr_g_kernel(const StepParams p, const BigR w) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, R = p.R, d = p.d;
+  if (c >= R) return;
+  const float* st = p.state;
+  const float iv = 1.0f / expf(st[p.lay.tr_logvar]);
+  const float* prow = st + p.lay.w_precision + (size_t)c * R;
+  const float* W = st + p.lay.w_mean;
+  float acc[VJF_MAX_XDIM];
+#pragma unroll
+  for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
+  for (int j = lane; j < R; j += 32) {
+    const float pv = prow[j];
+#pragma unroll
+    for (int k = 0; k < VJF_MAX_XDIM; ++k)
+      if (k < d) acc[k] = fmaf(pv, W[j * d + k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < VJF_MAX_XDIM; ++k) {
+    const float sum = warp_sum(acc[k]);
+    if (lane == 0 && k < d) {
+      float bsum = 0.f;
+      for (int z = 0; z < BIGR_BSPLIT; ++z) bsum += w.bstat[((size_t)z * R + c) * d + k];
+      w.M[(size_t)(R + k) * R + c] = fmaf(bsum, iv, sum);
+    }
   }
 }
 
@@ -355,63 +399,110 @@ __global__ void __launch_bounds__(256, 1) bigr_factor_kernel(const StepParams p,
   float* M = w.M;
   unsigned target = 0;
   const int nblk = (R + FB - 1) / FB;
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(w.ctl + 16);  // development aid: globaltimer of CTA 0 per panel phase
+#define BIGR_STAMP(i) if (blockIdx.x == 0 && tid == 0 && kb < 32) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[kb * 4 + (i)] = t_; }
   for (int kb = 0; kb < nblk; ++kb) {
     const int k0 = kb * FB, nbk = min(FB, R - k0);
-    // ---- L11 ----
-    for (int i = tid; i < FB * FB; i += 256) {
-      const int r = i >> 6, c = i & 63;
-      float v = (r == c) ? 1.0f : 0.f;
-      if (r < nbk && c <= r) v = __ldcg(M + (size_t)(k0 + r) * ld + k0 + c);
-      Ds[r * LD + c] = v;
+    BIGR_STAMP(0)
+    // ---- L11 = chol(A11) and U = L11^-T, every CTA redundantly.  The 64 x 64 block and an appended identity live in
+    //      registers (16 x 16 threads x 4 x 4 elements each); per column only the current column travels through shared memory
+    //      (double-buffered: one block barrier per column).  The appended rows receive the same column operations, i.e. they
+    //      end as I L11^-T. ----
+    const int ty = tid >> 4, tx = tid & 15;
+    float dv[4][4], ev[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = 4 * ty + a, c = 4 * tx + b;
+        dv[a][b] = (r < nbk && c <= r) ? __ldcg(M + (size_t)(k0 + r) * ld + k0 + c) : ((r == c) ? 1.0f : 0.f);
+        ev[a][b] = (r == c) ? 1.0f : 0.f;
+      }
+    float* colD = As;           // [2][64]   (As / Bs are free until the trailing update)
+    float* colE = As + 128;     // [2][64]
+#pragma unroll 1
+    for (int jb = 0; jb < 16; ++jb) {
+#pragma unroll
+      for (int cj = 0; cj < 4; ++cj) {
+        const int j = 4 * jb + cj, buf = (cj & 1) * 64;
+        if (tx == jb) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) { colD[buf + 4 * ty + a] = dv[a][cj]; colE[buf + 4 * ty + a] = ev[a][cj]; }
+        }
+        __syncthreads();
+        const float piv = colD[buf + j];
+        if (!(piv > 0.f) || !(piv < 1e37f)) {  // every CTA holds the same block: all of them leave together
+          if (blockIdx.x == 0 && tid == 0) { atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED); w.ctl[1] = 1u; }
+          return;
+        }
+        const float rs = 1.0f / sqrtf(piv);
+        float la[4], lb[4], le[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          la[a] = (4 * ty + a > j) ? colD[buf + 4 * ty + a] * rs : 0.f;
+          lb[a] = (4 * tx + a > j) ? colD[buf + 4 * tx + a] * rs : 0.f;
+          le[a] = colE[buf + 4 * ty + a] * rs;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) { dv[a][b] = fmaf(-la[a], lb[b], dv[a][b]); ev[a][b] = fmaf(-le[a], lb[b], ev[a][b]); }
+        if (tx == jb) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int r = 4 * ty + a;
+            dv[a][cj] = (r > j) ? la[a] : ((r == j) ? piv * rs : 0.f);
+            ev[a][cj] = le[a];
+          }
+        }
+      }
     }
     __syncthreads();
-    for (int j = 0; j < nbk; ++j) {
-      const float djj = Ds[j * LD + j];
-      if (!(djj > 0.f) || !(djj < 1e37f)) {  // every CTA holds the same block: all of them leave together
-        if (blockIdx.x == 0 && tid == 0) { atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED); w.ctl[1] = 1u; }
-        return;
+    float* Us = Bs;  // [64][65] U = L11^-T (upper triangular)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = 4 * ty + a, c = 4 * tx + b;
+        Ds[r * LD + c] = (c <= r) ? dv[a][b] : 0.f;
+        Us[r * LD + c] = (c >= r) ? ev[a][b] : 0.f;
       }
-      __syncthreads();
-      const float sd = sqrtf(djj), isd = 1.0f / sd;
-      if (tid == j) Ds[j * LD + j] = sd;
-      else if (tid > j && tid < nbk) Ds[tid * LD + j] *= isd;
-      __syncthreads();
-      const int nrem = nbk - j - 1;
-      for (int i = tid; i < nrem * nrem; i += 256) {
-        const int a = j + 1 + i / nrem, b = j + 1 + i % nrem;
-        if (b <= a) Ds[a * LD + b] = fmaf(-Ds[a * LD + j], Ds[b * LD + j], Ds[a * LD + b]);
-      }
-      __syncthreads();
-    }
+    __syncthreads();
     if (blockIdx.x == 0) {
       for (int i = tid; i < nbk * nbk; i += 256) {
         const int r = i / nbk, c = i - r * nbk;
         if (c <= r) M[(size_t)(k0 + r) * ld + k0 + c] = Ds[r * LD + c];
       }
     }
-    // ---- panel rows: [k0 + nbk, R + d + k0 + nbk) (the identity rows of later columns are still zero in this panel) ----
+    BIGR_STAMP(1)
+    // ---- panel rows [k0 + nbk, R + d + k0 + nbk) (the identity rows of later columns are still zero in this panel):
+    //      X <- X L11^-T = X U, one warp per row ----
     const int r_lo = k0 + nbk, nrows = R + d;
     {
       const int per = (nrows + gridDim.x - 1) / gridDim.x;
       const int my0 = blockIdx.x * per, my1 = min(nrows, my0 + per);
       for (int rr = my0 + warp; rr < my1; rr += 8) {
         float* rowp = M + (size_t)(r_lo + rr) * ld + k0;
-        float x0 = (lane < nbk) ? __ldcg(rowp + lane) : 0.f, x1 = (lane + 32 < nbk) ? __ldcg(rowp + lane + 32) : 0.f;
-        for (int j = 0; j < nbk; ++j) {
-          float s = 0.f;
-          if (lane < j) s = x0 * Ds[j * LD + lane];
-          if (lane + 32 < j) s = fmaf(x1, Ds[j * LD + lane + 32], s);
-          s = warp_sum(s);
-          const float inv = 1.0f / Ds[j * LD + j];
-          if (j < 32) { if (lane == j) x0 = (x0 - s) * inv; }
-          else if (lane == j - 32) x1 = (x1 - s) * inv;
+        const float x0 = (lane < nbk) ? __ldcg(rowp + lane) : 0.f, x1 = (lane + 32 < nbk) ? __ldcg(rowp + lane + 32) : 0.f;
+        float y0 = 0.f, y1 = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+          const float xc = __shfl_sync(0xffffffffu, x0, c);
+          y0 = fmaf(xc, Us[c * LD + lane], y0); y1 = fmaf(xc, Us[c * LD + lane + 32], y1);
         }
-        if (lane < nbk) rowp[lane] = x0;
-        if (lane + 32 < nbk) rowp[lane + 32] = x1;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+          const float xc = __shfl_sync(0xffffffffu, x1, c);
+          y1 = fmaf(xc, Us[(c + 32) * LD + lane + 32], y1);  // U[c + 32][lane] = 0 below the diagonal block
+        }
+        if (lane < nbk) rowp[lane] = y0;
+        if (lane + 32 < nbk) rowp[lane + 32] = y1;
       }
     }
     if (kb == nblk - 1) break;
+    BIGR_STAMP(2)
     grid_barrier(w.ctl, target);
+    BIGR_STAMP(3)
     // ---- trailing update: rows [r_lo, r_lo + R + d) x columns [r_lo, R) in 64 x 64 tiles ----
     {
       const int ncb = (R - r_lo + FB - 1) / FB, nrb = (nrows + FB - 1) / FB;
@@ -483,39 +574,51 @@ __global__ void __launch_bounds__(256, 1) bigr_factor_kernel(const StepParams p,
   }
 }
 
-// sum_b |dx - phi W|^2: one warp per trial, per-CTA partial sums in double
+// sum_b |dx - phi W|^2 (vjf/model.py:373-374): one warp per trial, W staged in shared memory, per-CTA partial sums in double
 __global__ void __launch_bounds__(256) bigr_resid_kernel(const StepParams p, const BigR w) {
+  extern __shared__ __align__(16) float Ws[];  // [R][d]
   __shared__ double red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = p.R, d = p.d;
-  const float* W = p.state + p.lay.w_mean;
+  for (int i = threadIdx.x; i < R * d; i += 256) Ws[i] = __ldcg(p.state + p.lay.w_mean + i);
+  __syncthreads();
   double tot = 0.0;
   for (int b = blockIdx.x * 8 + warp; b < p.B; b += gridDim.x * 8) {
     float acc[VJF_MAX_XDIM];
 #pragma unroll
     for (int k = 0; k < VJF_MAX_XDIM; ++k) acc[k] = 0.f;
     const float* ph = w.phi + (size_t)b * R;
-    for (int r = lane; r < R; r += 32) {
-      const float f = ph[r];
+    for (int r0 = 0; r0 < R; r0 += 256) {
+      float f[8];
 #pragma unroll
-      for (int k = 0; k < VJF_MAX_XDIM; ++k)
-        if (k < d) acc[k] = fmaf(f, __ldcg(W + r * d + k), acc[k]);
+      for (int i = 0; i < 8; ++i) { const int r = r0 + lane + 32 * i; f[i] = (r < R) ? ph[r] : 0.f; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + lane + 32 * i;
+        if (r < R) {
+#pragma unroll
+          for (int k = 0; k < VJF_MAX_XDIM; ++k)
+            if (k < d) acc[k] = fmaf(f[i], Ws[r * d + k], acc[k]);
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < VJF_MAX_XDIM; ++k) {
-      const float s = warp_sum(acc[k]);
-      if (k < d) { const float e = w.dx[(size_t)b * d + k] - s; tot += (double)e * (double)e; }
+      const float sum = warp_sum(acc[k]);
+      if (k < d) { const float e = w.dx[(size_t)b * d + k] - sum; tot += (double)e * (double)e; }
     }
   }
   if (lane == 0) red[warp] = tot;
   __syncthreads();
-  if (threadIdx.x == 0) { double s = 0.0; for (int i = 0; i < 8; ++i) s += red[i]; w.rpart[blockIdx.x] = s; }
+  if (threadIdx.x == 0) { double sum = 0.0; for (int i = 0; i < 8; ++i) sum += red[i]; w.rpart[blockIdx.x] = sum; }
 }
 
-// running state-noise variance (vjf/model.py:374-377, vjf/util.py:20-35)
+// running state-noise variance (vjf/model.py:374-377, vjf/util.py:20-35); the partial sums are added in a fixed order
 __global__ void bigr_noise_kernel(const StepParams p, const BigR w, int nparts) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
   double tot = 0.0;
-  for (int i = 0; i < nparts; ++i) tot += w.rpart[i];
+  for (int i = lane; i < nparts; i += 32) tot += w.rpart[i];
+  tot = warp_sum_d(tot);
+  if (lane != 0) return;
   float* st = p.state;
   const float mse = (float)(tot / ((double)p.Bglobal * (double)p.d));
   const double a = fmin((double)st[p.lay.tr_n], 500.0), n = a + (double)p.Bglobal;
@@ -568,15 +671,16 @@ int vjf_bigr_create(vjf_handle* h) {
   int bad = 0;
   bad |= alloc(&w->phi, B * R); bad |= alloc(&w->phiT, R * (size_t)w->Bp); bad |= alloc(&w->xs, B * d); bad |= alloc(&w->pm, B * d);
   bad |= alloc(&w->plv, B); bad |= alloc(&w->dx, B * d); bad |= alloc(&w->part1, (size_t)w->NP * B); bad |= alloc(&w->Ut, R * R);
-  bad |= alloc(&w->Apart, (size_t)w->SK * R * R); bad |= alloc(&w->bstat, R * d); bad |= alloc(&w->M, (2 * R + d) * R); bad |= alloc(&w->Pnew, R * R);
+  bad |= alloc(&w->Apart, (size_t)w->SK * R * R); bad |= alloc(&w->bstat, BIGR_BSPLIT * R * d); bad |= alloc(&w->M, (2 * R + d) * R); bad |= alloc(&w->Pnew, R * R);
   if (bad) { vjf_set_error("n_rbf=%d, max_trials=%d: out of device memory for the large-n_rbf workspace", p.R, h->cfg.max_trials); return -2; }
   VJF_CUDA_OK(cudaMalloc(&w->rpart, 1024 * sizeof(double)));
-  VJF_CUDA_OK(cudaMalloc(&w->ctl, 64));
-  VJF_CUDA_OK(cudaMemset(w->ctl, 0, 64));
+  VJF_CUDA_OK(cudaMalloc(&w->ctl, 4096));
+  VJF_CUDA_OK(cudaMemset(w->ctl, 0, 4096));
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bg::SMEM_BYTES));
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
+  VJF_CUDA_OK(cudaFuncSetAttribute(bigr_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->smem_limit - 1024, R * d * sizeof(float) + 64)));
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * 65 * 4));
-  const size_t feat = (32 * (R + 1) + 32 * (size_t)p.du) * 4;
+  const size_t feat = (BIGR_FT * (R + 1) + BIGR_FT * (size_t)p.du + 4 + R * d) * 4;
   if (feat > h->smem_limit) { vjf_set_error("n_rbf=%d too large for the feature tile in shared memory", p.R); return -1; }
   return 0;
 }
@@ -590,7 +694,20 @@ void vjf_bigr_destroy(vjf_handle* h) {
   h->bigr = nullptr;
 }
 
+// development aid: VJF_BIGR_TIMING=1 prints the CUDA-event time of every launch of the last time step to stderr
+struct BigrTimer {
+  bool on; cudaStream_t s; cudaEvent_t ev[32]; const char* name[32]; int n;
+  void mark(const char* nm) { if (!on || n >= 32) return; if (!ev[n]) cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], s); name[n++] = nm; }
+  void report() {
+    if (!on || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    for (int i = 0; i + 1 < n; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, "  bigr %-10s %8.1f us\n", name[i], ms * 1e3f); }
+  }
+};
+
 int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t s) {
+  static BigrTimer tm = {getenv("VJF_BIGR_TIMING") != nullptr, nullptr, {}, {}, 0};
+  tm.s = s;
   BigR& w = *h->bigr;
   if (B > w.Bmax) { vjf_set_error("trials B=%d above max_trials=%d", B, w.Bmax); return -1; }
   if (p0.y_dtype != VJF_Y_F32 && p0.y_dtype != VJF_Y_U8) { vjf_set_error("unknown y dtype"); return -1; }
@@ -605,7 +722,7 @@ int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
   // w_chol^T from the state (the caller may have loaded a new state since the last launch)
   bigr_transpose_kernel<<<dim3((R + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(h->state + pl.lay.w_chol, w.Ut, R);
   ++g_vjf_launches;
-  const size_t feat_smem = (32 * ((size_t)R + 1) + 32 * (size_t)pl.du) * 4;
+  const size_t feat_smem = (BIGR_FT * ((size_t)R + 1) + BIGR_FT * (size_t)pl.du + 4 + (size_t)R * d) * 4;
   const size_t ysz = (pl.y_dtype == VJF_Y_U8) ? 1 : 4;
   const bool upd = pl.flags & VJF_FLAG_UPDATE, warm = pl.flags & VJF_FLAG_WARMUP;
   const int nb_grid = std::max(1, std::min(h->num_sms, (pl.lay.n_train + VJF_NT - 1) / VJF_NT));
@@ -619,15 +736,22 @@ int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     p.losses = pl.losses ? pl.losses + (size_t)t * 4 : nullptr;
     if (t > 0) { p.q0m = pl.mu + (size_t)(t - 1) * B * d; p.q0l = pl.logvar + (size_t)(t - 1) * B * d; p.flags = pl.flags & ~(uint32_t)VJF_FLAG_PRIOR_Q0; }
     p.step0 = pl.step0 + t;
-    bigr_feat_kernel<<<(B + 31) / 32, 512, feat_smem, s>>>(p, w, 0);
+    tm.n = 0;
+    tm.mark("feat");
+    bigr_feat_kernel<<<(B + BIGR_FT - 1) / BIGR_FT, 512, feat_smem, s>>>(p, w, 0);
+    tm.mark("gemm1");
     {
       bg::Args g = {B, R, R, 1, 0, 0, w.part1, w.Bmax};
       bigr_gemm_kernel<<<dim3((B + bg::BM - 1) / bg::BM, (R + bg::BN - 1) / bg::BN, 1), bg::NT, bg::SMEM_BYTES, s>>>(mPhi, mUt, g);
     }
+    tm.mark("plv");
     bigr_plv_kernel<<<(B + 255) / 256, 256, 0, s>>>(w, B);
+    tm.mark("phase_a");
     vjf_phase_a_kernel<<<p.nslots, VJF_NT, (size_t)p.s_total * sizeof(float), s>>>(p);
     g_vjf_launches += 4;
+    tm.mark("reduce");
     if (vjf_internal_reduce(p, s)) return -2;
+    tm.mark("phase_b");
     {
       StepParams pb = p;
       pb.B = B;
@@ -636,21 +760,29 @@ int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     }
     if (upd) {
       if (!warm) {
+        tm.mark("gemm2");
         bg::Args g = {R, R, B, 0, 1, 1, w.Apart, R};
         bigr_gemm_kernel<<<dim3((R + bg::BM - 1) / bg::BM, (R + bg::BN - 1) / bg::BN, w.SK), bg::NT, bg::SMEM_BYTES, s>>>(mPhiT_a, mPhiT_b, g);
-        bigr_bstat_kernel<<<(R + 7) / 8, 256, 0, s>>>(p, w);
+        tm.mark("bstat");
+        bigr_bstat_kernel<<<dim3((R + 7) / 8, BIGR_BSPLIT), 256, 0, s>>>(p, w);
+        tm.mark("g+setup");
+        bigr_g_kernel<<<(R + 7) / 8, 256, 0, s>>>(p, w);  // reads the old w_precision: before the commit of the factorisation
         bigr_setup_kernel<<<h->num_sms * 4, 256, 0, s>>>(p, w);
+        tm.mark("factor");
         VJF_CUDA_OK(cudaMemsetAsync(w.ctl, 0, 8, s));
         void* args[] = {(void*)&p, (void*)&w};
         VJF_CUDA_OK(cudaLaunchCooperativeKernel((void*)bigr_factor_kernel, dim3(h->num_sms), dim3(256), args, (size_t)3 * 64 * 65 * 4, s));
-        g_vjf_launches += 4;
+        g_vjf_launches += 5;
       }
-      const int nparts = std::min(1024, std::max(1, (B + 7) / 8));
-      bigr_resid_kernel<<<nparts, 256, 0, s>>>(p, w);
+      const int nparts = std::min(4 * h->num_sms, std::max(1, (B + 7) / 8));
+      tm.mark("resid");
+      bigr_resid_kernel<<<nparts, 256, (size_t)R * d * sizeof(float), s>>>(p, w);
       bigr_noise_kernel<<<1, 32, 0, s>>>(p, w, nparts);
       g_vjf_launches += 2;
     }
+    tm.mark("end");
   }
+  tm.report();
   VJF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -658,5 +790,5 @@ int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
 // views of the large-n_rbf workspace (tests / profiling): 0 phi [B][R], 1 p_mean [B][d], 2 p_logvar [B], 3 phi^T phi partial sums
 extern "C" float* vjf_bigr_buffer(vjf_handle* h, int32_t which) {
   if (!h || !h->bigr) return nullptr;
-  switch (which) { case 0: return h->bigr->phi; case 1: return h->bigr->pm; case 2: return h->bigr->plv; case 3: return h->bigr->Apart; default: return nullptr; }
+  switch (which) { case 4: return reinterpret_cast<float*>(h->bigr->ctl); case 0: return h->bigr->phi; case 1: return h->bigr->pm; case 2: return h->bigr->plv; case 3: return h->bigr->Apart; default: return nullptr; }
 }
