@@ -196,18 +196,19 @@ __global__ void __launch_bounds__(512) bigr_feat_kernel(const StepParams p, cons
   extern __shared__ __align__(16) float sm[];
   constexpr int FT = BIGR_FT;
   const int tid = threadIdx.x, R = p.R, d = p.d, u = p.u, du = p.du, ldt = R + 1;
-  float* tile = sm;                 // [FT][R + 1]
-  float* xu_s = tile + FT * ldt;    // [FT][du]
-  float* Wt = xu_s + ((FT * du + 3) & ~3);  // [d][R]  w_mean transposed: conflict-free reads with the lanes over the RBFs
+  const int du4 = (du + 3) >> 2, ldx = 4 * du4;  // rows of xu padded with zeros to whole float4 groups
+  float* xu_s = sm;                 // [FT][ldx]  (first: 16-byte aligned)
+  float* tile = xu_s + FT * ldx;    // [FT][R + 1]
+  float* Wt = tile + ((FT * ldt + 3) & ~3);  // [d][R]  w_mean transposed: conflict-free reads with the lanes over the RBFs
   const int b0 = blockIdx.x * FT, nb = min(FT, p.B - b0);
   const float* st = p.state;
   const bool prior = (t == 0) && (p.flags & VJF_FLAG_PRIOR_Q0);
   const float* qm = (t == 0) ? p.q0m : p.mu + (size_t)(t - 1) * p.B * d;
   const float* ql = (t == 0) ? p.q0l : p.logvar + (size_t)(t - 1) * p.B * d;
-  for (int i = tid; i < FT * du; i += blockDim.x) {
-    const int b = i / du, k = i - b * du;
+  for (int i = tid; i < FT * ldx; i += blockDim.x) {
+    const int b = i / ldx, k = i - b * ldx;
     float v = 0.f;
-    if (b < nb) {
+    if (b < nb && k < du) {
       if (k < d) {
         const float m = prior ? st[p.lay.prior_mean + k] : qm[(size_t)(b0 + b) * d + k];
         const float l = prior ? st[p.lay.prior_logvar + k] : ql[(size_t)(b0 + b) * d + k];
@@ -226,17 +227,55 @@ __global__ void __launch_bounds__(512) bigr_feat_kernel(const StepParams p, cons
   __syncthreads();
   const float* cen = st + p.lay.centroid;
   const float* lw = st + p.lay.logwidth;
+  if (du4 <= 4) {
+    // two RBFs per thread with their centres in registers; a trial's inputs arrive as (broadcast) 128-bit shared-memory loads
+    for (int rb = 0; rb < R; rb += 2 * blockDim.x) {
+      const int r0 = rb + tid, r1 = rb + tid + blockDim.x;
+      float4 c0[4], c1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float t0[4], t1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 4 * q + e;
+          t0[e] = (q < du4 && k < du && r0 < R) ? cen[r0 * du + k] : 0.f;
+          t1[e] = (q < du4 && k < du && r1 < R) ? cen[r1 * du + k] : 0.f;
+        }
+        c0[q] = make_float4(t0[0], t0[1], t0[2], t0[3]); c1[q] = make_float4(t1[0], t1[1], t1[2], t1[3]);
+      }
+      float iw0 = 0.f, iw1 = 0.f;
+      if (r0 < R) { const float wd = expf(lw[r0]); iw0 = -0.5f / (wd * wd); }
+      if (r1 < R) { const float wd = expf(lw[r1]); iw1 = -0.5f / (wd * wd); }
+#pragma unroll 2
+      for (int b = 0; b < FT; ++b) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < du4) {
+            const float4 x = *reinterpret_cast<const float4*>(xu_s + b * ldx + 4 * q);
+            float df;
+            df = x.x - c0[q].x; a0 = fmaf(df, df, a0); df = x.y - c0[q].y; a0 = fmaf(df, df, a0);
+            df = x.z - c0[q].z; a0 = fmaf(df, df, a0); df = x.w - c0[q].w; a0 = fmaf(df, df, a0);
+            df = x.x - c1[q].x; a1 = fmaf(df, df, a1); df = x.y - c1[q].y; a1 = fmaf(df, df, a1);
+            df = x.z - c1[q].z; a1 = fmaf(df, df, a1); df = x.w - c1[q].w; a1 = fmaf(df, df, a1);
+          }
+        const bool live = b < nb;
+        const float v0 = live ? expf(a0 * iw0) : 0.f, v1 = live ? expf(a1 * iw1) : 0.f;
+        if (r0 < R) { if (live) w.phi[(size_t)(b0 + b) * R + r0] = v0; tile[b * ldt + r0] = v0; }
+        if (r1 < R) { if (live) w.phi[(size_t)(b0 + b) * R + r1] = v1; tile[b * ldt + r1] = v1; }
+      }
+    }
+  } else
   for (int r = tid; r < R; r += blockDim.x) {
     float c[2 * VJF_MAX_XDIM];
     for (int k = 0; k < du; ++k) c[k] = cen[r * du + k];
     const float wd = expf(lw[r]);
     const float iw = -0.5f / (wd * wd);
-#pragma unroll 4
     for (int b = 0; b < FT; ++b) {
       float v = 0.f;
       if (b < nb) {
         float d2 = 0.f;
-        for (int k = 0; k < du; ++k) { const float df = xu_s[b * du + k] - c[k]; d2 = fmaf(df, df, d2); }
+        for (int k = 0; k < du; ++k) { const float df = xu_s[b * ldx + k] - c[k]; d2 = fmaf(df, df, d2); }
         v = expf(d2 * iw);
         w.phi[(size_t)(b0 + b) * R + r] = v;
       }
@@ -263,7 +302,7 @@ __global__ void __launch_bounds__(512) bigr_feat_kernel(const StepParams p, cons
 #pragma unroll
     for (int k = 0; k < VJF_MAX_XDIM; ++k) {
       const float sum = warp_sum(acc[k]);
-      if (lane == 0 && k < d && b < nb) w.pm[(size_t)(b0 + b) * d + k] = xu_s[b * du + k] + sum;
+      if (lane == 0 && k < d && b < nb) w.pm[(size_t)(b0 + b) * d + k] = xu_s[b * ldx + k] + sum;
     }
   }
 }
@@ -435,7 +474,8 @@ __global__ void __launch_bounds__(256, 1) bigr_factor_kernel(const StepParams p,
           if (blockIdx.x == 0 && tid == 0) { atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED); w.ctl[1] = 1u; }
           return;
         }
-        const float rs = 1.0f / sqrtf(piv);
+        float rs = rsqrtf(piv);
+        rs = rs * fmaf(-0.5f * piv, rs * rs, 1.5f);  // one Newton step: < 1 ulp, off the slow division path
         float la[4], lb[4], le[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -512,10 +552,22 @@ __global__ void __launch_bounds__(256, 1) bigr_factor_kernel(const StepParams p,
         const int nr = min(FB, r_lo + nrows - row0), nc = min(FB, R - col0);
         if (row0 + nr - 1 < col0 && row0 + nr - 1 < R) continue;  // a tile of P' entirely above the diagonal
         __syncthreads();
-        for (int i = tid; i < FB * FB; i += 256) {
-          const int r = i >> 6, c = i & 63;
-          As[r * LD + c] = (r < nr && c < nbk) ? __ldcg(M + (size_t)(row0 + r) * ld + k0 + c) : 0.f;
-          Bs[r * LD + c] = (r < nc && c < nbk) ? __ldcg(M + (size_t)(col0 + r) * ld + k0 + c) : 0.f;
+        {
+          float4 va[4], vb[4];
+          const int c4 = (tid & 15) << 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (tid >> 4) + 16 * i;
+            va[i] = (r < nr && c4 < nbk) ? __ldcg(reinterpret_cast<const float4*>(M + (size_t)(row0 + r) * ld + k0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[i] = (r < nc && c4 < nbk) ? __ldcg(reinterpret_cast<const float4*>(M + (size_t)(col0 + r) * ld + k0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (tid >> 4) + 16 * i;
+            float* ap = As + r * LD + c4; float* bp = Bs + r * LD + c4;
+            ap[0] = va[i].x; ap[1] = va[i].y; ap[2] = va[i].z; ap[3] = va[i].w;
+            bp[0] = vb[i].x; bp[1] = vb[i].y; bp[2] = vb[i].z; bp[3] = vb[i].w;
+          }
         }
         __syncthreads();
         const int ty = tid >> 4, tx = tid & 15;
@@ -533,15 +585,16 @@ __global__ void __launch_bounds__(256, 1) bigr_factor_kernel(const StepParams p,
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
         }
+        if (tx * 4 + 3 < nc) {  // R is a multiple of 4 and so are col0 and k0: whole float4 groups
+          float4 cv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int r = ty * 4 + a;
-          if (r >= nr) continue;
+          for (int a = 0; a < 4; ++a)
+            cv[a] = (ty * 4 + a < nr) ? __ldcg(reinterpret_cast<const float4*>(M + (size_t)(row0 + ty * 4 + a) * ld + col0 + tx * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int c = tx * 4 + b;
-            if (c < nc) { float* o = M + (size_t)(row0 + r) * ld + col0 + c; *o = __ldcg(o) - acc[a][b]; }
-          }
+          for (int a = 0; a < 4; ++a)
+            if (ty * 4 + a < nr)
+              *reinterpret_cast<float4*>(M + (size_t)(row0 + ty * 4 + a) * ld + col0 + tx * 4) =
+                  make_float4(cv[a].x - acc[a][0], cv[a].y - acc[a][1], cv[a].z - acc[a][2], cv[a].w - acc[a][3]);
         }
       }
     }
@@ -664,7 +717,7 @@ int vjf_bigr_create(vjf_handle* h) {
   BigR* w = (BigR*)calloc(1, sizeof(BigR));
   h->bigr = w;
   const size_t B = (size_t)h->cfg.max_trials, R = (size_t)p.R, d = (size_t)p.d;
-  w->Bmax = (int)B; w->Bp = (int)((B + 3) & ~(size_t)3);
+  w->Bmax = (int)B; w->Bp = (int)((B + 3) & ~(size_t)3) + 32;  // + 128 bytes: a power-of-two row pitch would put every row of a tile on the same L2 slice / channel
   w->NP = 2 * (int)((R + bg::BN - 1) / bg::BN);
   w->SK = 7;
   auto alloc = [&](float** ptr, size_t n) { if (cudaMalloc(ptr, n * sizeof(float)) != cudaSuccess) return -1; return cudaMemset(*ptr, 0, n * sizeof(float)) == cudaSuccess ? 0 : -1; };
@@ -680,7 +733,7 @@ int vjf_bigr_create(vjf_handle* h) {
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->smem_limit - 1024, R * d * sizeof(float) + 64)));
   VJF_CUDA_OK(cudaFuncSetAttribute(bigr_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * 65 * 4));
-  const size_t feat = (BIGR_FT * (R + 1) + BIGR_FT * (size_t)p.du + 4 + R * d) * 4;
+  const size_t feat = (BIGR_FT * (R + 1) + BIGR_FT * (size_t)(p.du + 3) + 8 + R * d) * 4;
   if (feat > h->smem_limit) { vjf_set_error("n_rbf=%d too large for the feature tile in shared memory", p.R); return -1; }
   return 0;
 }
@@ -722,7 +775,7 @@ int vjf_bigr_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
   // w_chol^T from the state (the caller may have loaded a new state since the last launch)
   bigr_transpose_kernel<<<dim3((R + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(h->state + pl.lay.w_chol, w.Ut, R);
   ++g_vjf_launches;
-  const size_t feat_smem = (BIGR_FT * ((size_t)R + 1) + BIGR_FT * (size_t)pl.du + 4 + (size_t)R * d) * 4;
+  const size_t feat_smem = (BIGR_FT * ((size_t)R + 1) + BIGR_FT * (size_t)(pl.du + 3) + 8 + (size_t)R * d) * 4;
   const size_t ysz = (pl.y_dtype == VJF_Y_U8) ? 1 : 4;
   const bool upd = pl.flags & VJF_FLAG_UPDATE, warm = pl.flags & VJF_FLAG_WARMUP;
   const int nb_grid = std::max(1, std::min(h->num_sms, (pl.lay.n_train + VJF_NT - 1) / VJF_NT));
