@@ -45,10 +45,10 @@ def test_c5_shapes_2000_steps_match_fp64_oracle(bits):
     assert got["likelihood.n_sample"] == want["likelihood.n_sample"] and got["transition.n_sample"] == want["transition.n_sample"]
 
 
-def test_fp64_rls_solves_an_ill_conditioned_initialisation_fp32_cannot():
-    """RBFDS.initialize on few samples with overlapping RBFs: phi^T phi is close to singular.  In fp32 the factorisation either
-    fails (Cholesky pivot <= 0 -> 'RLS failed.'; the reference's fp32 fallback calls the removed torch.eig, vjf/module.py:104-112)
-    or returns weights far from the fp64 solution; the double-precision recursion matches the fp64 oracle's predictions."""
+def test_rls_initialisation_on_few_samples_fp64_and_fp32():
+    """RBFDS.initialize on fewer samples than RBFs (phi^T phi is rank deficient, only the prior term keeps P' positive definite):
+    the double-precision recursion matches the fp64 oracle's predictions; the fp32 one either reports a failed factorisation
+    (Cholesky pivot <= 0 -> 'RLS failed.', vjf/module.py:104-112) or is equally close."""
     import warnings
     from vjf_b200.model import VJF
     dev = torch.device("cuda")
@@ -71,7 +71,9 @@ def test_fp64_rls_solves_an_ill_conditioned_initialisation_fp32_cannot():
         if bits == 64:
             assert_close(m.transition.logvar.item(), o.tr_logvar, 1e-3, 1e-3, "transition.logvar")
     assert status[64] == 0 and err[64] < 1e-4 * max(1.0, float(np.abs(want).max())), (status, err)
-    assert (status[32] & 16) or err[32] > 10 * err[64], (status, err)
+    # fp32: a failed factorisation is reported (status bit 16, 'RLS failed.'), otherwise the result must be as good as the double one
+    # up to the fp32 statistics both share
+    assert (status[32] & 16) or err[32] < 1e-3 * max(1.0, float(np.abs(want).max())), (status, err)
 
 
 def test_fp64_rls_keeps_the_weights_bounded_over_6000_steps_at_bench_scale():
