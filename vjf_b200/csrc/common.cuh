@@ -324,6 +324,7 @@ struct vjf_handle {
   float* fc_w; size_t fc_w_sz;  // forecast: sampled weights of every step (grow-only)
   double* P64;                   // double shadow of w_precision (vjf_set_rls_precision)
   struct BigR* bigr;             // workspace of the large-n_rbf path (bigr.cu)
+  struct Wide* wide;             // workspace of the wide-observation path (wide.cu)
   double* wk_ws; size_t wk_ws_sz;  // weight-space Kalman update: fp64 R x R workspace (grow-only)
   float* w1k; float* uk;         // operand images of the tile pipeline
 };

@@ -21,3 +21,13 @@ void vjf_bigr_destroy(vjf_handle* h);
 int vjf_bigr_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s);
 int vjf_plan_tiles_public(vjf_handle* h, StepParams& p, int B);
 int vjf_internal_reduce(const StepParams& p, cudaStream_t s);
+
+// wide observations (wide.cu; ydim above the tile pipeline's limit): per-step launch sequence with the two contractions over the
+// observation columns as tcgen05 GEMMs over all trials
+int vjf_wide_create(vjf_handle* h);
+void vjf_wide_destroy(vjf_handle* h);
+bool vjf_wide_applies(vjf_handle* h, const StepParams& p, int B);
+int vjf_wide_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStream_t s);
+// are all observations exactly representable in tf32 (spike counts)?  (tile_host.cu; synchronises the stream)
+int vjf_observations_exact(vjf_handle* h, const void* y, size_t n, cudaStream_t s, bool* exact);
+int vjf_tile_mode_get();  // vjf_set_tile_mode: 1 = general persistent kernel only (no tile pipeline, no wide-observation path)

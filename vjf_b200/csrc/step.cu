@@ -265,6 +265,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
   }
   if (vjf_tile_create(h)) return -2;
   if (p.ext && vjf_bigr_create(h)) return -2;
+  if (vjf_wide_create(h)) return -2;
   *out = h;
   return 0;
 }
@@ -279,7 +280,7 @@ extern "C" int vjf_destroy(vjf_handle* h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
-  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w); cudaFree(h->wk_ws); cudaFree(h->P64); vjf_bigr_destroy(h);
+  cudaFree(h->stage_mu); cudaFree(h->stage_lv); cudaFree(h->stage_loss); cudaFree(h->fc_w); cudaFree(h->wk_ws); cudaFree(h->P64); vjf_bigr_destroy(h); vjf_wide_destroy(h);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   free(h);
@@ -345,6 +346,7 @@ static int launch_time_loop(vjf_handle* h, StepParams& p, int T, int B, cudaStre
   if (use_tile < 0) return -2;
   g_vjf_last_kind = use_tile ? 1 : 0;
   if (use_tile) return vjf_tile_launch(h, p, map, s);
+  if (vjf_wide_applies(h, p, B)) { g_vjf_last_kind = 3; return vjf_wide_time_loop(h, p, T, B, s); }
   if (plan_tiles(h, p, B, h->max_slots, 1)) return -1;
   return launch_persistent(h, p, s);
 }

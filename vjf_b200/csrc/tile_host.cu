@@ -13,6 +13,7 @@ static inline int rup(int v, int a) { return (v + a - 1) / a * a; }
 // 0: automatic; 1: never use the tile pipeline; 2: tile pipeline without the exact-observation mode; 3: 64-trial tiles whenever
 // the observations are exact (tests drive every variant through the same process)
 static int g_tile_mode = 0;
+int vjf_tile_mode_get() { return g_tile_mode; }
 extern "C" int vjf_set_tile_mode(int32_t mode) {
   if (mode < 0 || mode > 3) { vjf_set_error("tile mode must be 0..3"); return -1; }
   g_tile_mode = mode;
@@ -47,7 +48,7 @@ __global__ void vjf_y_exact_kernel(const float4* __restrict__ y, size_t n4, cons
   if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
-static int observations_exact(vjf_handle* h, const void* y, size_t n, cudaStream_t s, bool* exact) {
+int vjf_observations_exact(vjf_handle* h, const void* y, size_t n, cudaStream_t s, bool* exact) {
   unsigned* flag = h->sync_words + 48;
   VJF_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(unsigned), s));
   const size_t n4 = n / 4;
@@ -113,7 +114,7 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   const bool no_exact = no_exact_env || g_tile_mode == 2;
   // spike counts (Poisson likelihood): are they exact in tf32?
   bool exact = false;
-  if (p.lik == VJF_LIK_POISSON && !no_exact && observations_exact(h, y, (size_t)T * B * D, stream, &exact)) return -1;
+  if (p.lik == VJF_LIK_POISSON && !no_exact && vjf_observations_exact(h, y, (size_t)T * B * D, stream, &exact)) return -1;
   pl.CL0 = exact ? D / 32 : 0;
   pl.NBLKLO = pl.NBLK - pl.CL0 / 4;  // lo accumulator blocks, aligned with the blocks CL0 / 4 .. of the hi part
   // tiles of 32 trials; 64 when the lo image is small (exact observations) and every trial CTA gets more than one tile
