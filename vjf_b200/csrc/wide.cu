@@ -208,8 +208,8 @@ constexpr int WM_TB = 32;   // trials per sub-tile
 constexpr int WM_NC = 4;    // observation columns per thread (ydim <= 4 * 512)
 
 struct WideSm {  // float offsets
-  int hs, gp, phi, U, Wm, cen, iw, W1e, hm, hv, dec, ex, eps, xu, xt, mt, lt, pm, dx, gxt, gmt, glt, plv, gxp, red, total;
-  int HP, RP, U_in;
+  int hs, gp, phi, U, Wm, cen, iw, W1e, hm, hv, dec, ex, eps, xu, xt, mt, lt, pm, dx, gxt, gmt, glt, plv, gxp, red, xt8, gm8, gl8, total;
+  int HP, RP, EP, U_in;
 };
 
 static inline WideSm wide_plan(const StepParams& p, bool u_in) {
@@ -217,18 +217,19 @@ static inline WideSm wide_plan(const StepParams& p, bool u_in) {
   int f = 0;
   auto take = [&](int n) { int at = f; f = (f + n + 3) & ~3; return at; };
   const int d = p.d, H = p.H[0], R = p.R, TB = WM_TB;
-  s.HP = H + 1; s.RP = R + 1; s.U_in = u_in ? 1 : 0;
+  s.HP = H + 1; s.RP = R + 1; s.EP = std::max(4, (p.E + 3) & ~3); s.U_in = u_in ? 1 : 0;
   s.hs = take(TB * s.HP); s.gp = take(TB * s.HP); s.phi = take(TB * s.RP);
   s.U = take(u_in ? R * R : 4);
   s.Wm = take(R * d); s.cen = take(R * p.du); s.iw = take(R);
   s.W1e = take((p.E + 1) * H);
   s.hm = take(H * d); s.hv = take(H * d + d);
-  s.dec = take((d + 1) * p.D);
-  s.ex = take(TB * std::max(p.E, 1)); s.eps = take(TB * 2 * d); s.xu = take(TB * p.du);
+  s.dec = take(12 * p.D);  // per observation column: 8 decoder weights (zero padded), bias, 3 pad
+  s.ex = take(TB * s.EP); s.eps = take(TB * 2 * d); s.xu = take(TB * p.du);
   s.xt = take(TB * d); s.mt = take(TB * d); s.lt = take(TB * d); s.pm = take(TB * d); s.dx = take(TB * d);
   s.gxt = take(TB * d); s.gmt = take(TB * d); s.glt = take(TB * d); s.plv = take(TB);
   s.gxp = take(VJF_NWARP * TB * 8);
   s.red = take(VJF_NWARP * VJF_NSCAL + 16);
+  s.xt8 = take(TB * 8); s.gm8 = take(TB * 8); s.gl8 = take(TB * 8);  // rows padded to 8: 128-bit broadcast loads
   s.total = f;
   return s;
 }
@@ -239,13 +240,14 @@ template <int LIK>
 __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p, const Wide w, const WideSm s) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, H = p.H[0], HP = s.HP, RP = s.RP, B = p.B;
+  const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, H = p.H[0], HP = s.HP, RP = s.RP, EP = s.EP, B = p.B;
   constexpr int TB = WM_TB;
   float* hs = sm + s.hs;   float* gp = sm + s.gp;   float* phi = sm + s.phi; float* U_s = sm + s.U;  float* Wm = sm + s.Wm;
   float* cen = sm + s.cen; float* iw = sm + s.iw;   float* W1e = sm + s.W1e; float* hm = sm + s.hm;  float* hv = sm + s.hv;
   float* dec = sm + s.dec; float* ex = sm + s.ex;   float* eps_s = sm + s.eps; float* xu = sm + s.xu; float* xt_s = sm + s.xt;
   float* mt_s = sm + s.mt; float* lt_s = sm + s.lt; float* pm_s = sm + s.pm; float* dx_s = sm + s.dx; float* gxt_s = sm + s.gxt;
   float* gmt_s = sm + s.gmt; float* glt_s = sm + s.glt; float* plv_s = sm + s.plv; float* gxp = sm + s.gxp; float* red_s = sm + s.red;
+  float* xt8 = sm + s.xt8; float* gm8 = sm + s.gm8; float* gl8 = sm + s.gl8;
   float* st = p.state;
   float* slot = p.partials + (size_t)blockIdx.x * p.PS;
   const bool r_on = true, d_on = !(p.flags & VJF_FLAG_WARMUP), h_on = true;
@@ -259,8 +261,10 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
   for (int i = tid; i < H; i += VJF_NT) W1e[E * H + i] = st[p.lay.mlp_b[0] + i];
   for (int i = tid; i < H * d; i += VJF_NT) { hm[i] = st[p.lay.head_m_w + i]; hv[i] = st[p.lay.head_v_w + i]; }
   for (int i = tid; i < d; i += VJF_NT) hv[H * d + i] = st[p.lay.head_v_b + i];
-  for (int i = tid; i < d * D; i += VJF_NT) dec[i] = st[p.lay.dec_w + i];
-  for (int i = tid; i < D; i += VJF_NT) dec[d * D + i] = st[p.lay.dec_b + i];
+  for (int i = tid; i < 8 * D; i += VJF_NT) { const int k = i / D, j = i - k * D; dec[j * 12 + k] = (k < d) ? st[p.lay.dec_w + i] : 0.f; }
+  for (int i = tid; i < D; i += VJF_NT) dec[i * 12 + 8] = st[p.lay.dec_b + i];
+  for (int i = tid; i < TB * 8; i += VJF_NT) { xt8[i] = 0.f; gm8[i] = 0.f; gl8[i] = 0.f; }
+  for (int i = tid; i < TB * EP; i += VJF_NT) ex[i] = 0.f;
   float lam = 0.f;
   if (LIK == VJF_LIK_GAUSSIAN) lam = st[p.lay.lik_logvar];
   const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
         else { ms = p.q0m[(size_t)(b0 + b) * d + k]; ls = p.q0l[(size_t)(b0 + b) * d + k]; }
         if (p.eps) { eps_s[b * 2 * d + k] = p.eps[(size_t)(b0 + b) * d + k]; eps_s[b * 2 * d + d + k] = p.eps[((size_t)B + b0 + b) * d + k]; }
       } else { eps_s[b * 2 * d + k] = 0.f; eps_s[b * 2 * d + d + k] = 0.f; }
-      ex[b * E + u + k] = ms; ex[b * E + u + d + k] = ls;
+      ex[b * EP + u + k] = ms; ex[b * EP + u + d + k] = ls;
     }
     if (!p.eps) {
       const int nblk = (d + 3) >> 2;
@@ -307,12 +311,12 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
     }
     for (int i = tid; i < TB * u; i += VJF_NT) {
       const int b = i / u, e = i - b * u;
-      ex[b * E + e] = (b < nb) ? p.u_in[(size_t)(b0 + b) * u + e] : 0.f;
+      ex[b * EP + e] = (b < nb) ? p.u_in[(size_t)(b0 + b) * u + e] : 0.f;
     }
     __syncthreads();
     for (int i = tid; i < TB * du; i += VJF_NT) {
       const int b = i / du, k = i - b * du;
-      xu[i] = (k < d) ? ex[b * E + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * ex[b * E + u + d + k]) : ex[b * E + (k - d)];
+      xu[i] = (k < d) ? ex[b * EP + u + k] + eps_s[b * 2 * d + k] * expf(0.5f * ex[b * EP + u + d + k]) : ex[b * EP + (k - d)];
     }
     __syncthreads();
     // ---- S1: RBF features (vjf/functional.py:11-22) ; S2: h = tanh(in W1 + b1) (vjf/recognition.py:38-40) with the observation part
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
       if (b < nb) {
         float a = W1e[E * H + n];
         for (int z = 0; z < w.ZF; ++z) a += w.pre[((size_t)z * B + b0 + b) * H + n];
-        for (int e = 0; e < E; ++e) a = fmaf(ex[b * E + e], W1e[e * H + n], a);
+        for (int e = 0; e < E; ++e) a = fmaf(ex[b * EP + e], W1e[e * H + n], a);
         v = tanhf(a);
       }
       hs[b * HP + n] = v;
@@ -361,24 +365,29 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
           p.mu[(size_t)(b0 + b) * d + k] = m;
           p.logvar[(size_t)(b0 + b) * d + k] = lv;
         } else { m = 0.f; lv = 0.f; }
-        mt_s[bk] = m; lt_s[bk] = lv; xt_s[bk] = x; dx_s[bk] = dxv;
+        mt_s[bk] = m; lt_s[bk] = lv; xt_s[bk] = x; dx_s[bk] = dxv; xt8[b * 8 + k] = x;
       }
     }
     // ---- S4: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W, p_logvar = log |phi w_chol|^2 ----
+    {  // FL[b][n] = sum_r phi[b][r] w_chol[r][n]: a thread owns one column n for four trials (one load of w_chol per four FMAs)
+      const float* Ug = s.U_in ? U_s : st + p.lay.w_chol;
+      for (int it = tid; it < R * (TB / 4); it += VJF_NT) {
+        const int bg = it / R, n = it - bg * R;
+        const float* ph = phi + (4 * bg) * RP;
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+          const float uv = Ug[r * R + n];
+          f0 = fmaf(ph[r], uv, f0); f1 = fmaf(ph[RP + r], uv, f1); f2 = fmaf(ph[2 * RP + r], uv, f2); f3 = fmaf(ph[3 * RP + r], uv, f3);
+        }
+        float* o = gxp + (4 * bg) * 128 + n;  // (scratch: the g_xt partial sums are not live yet)
+        o[0] = f0 * f0; o[128] = f1 * f1; o[256] = f2 * f2; o[384] = f3 * f3;
+      }
+    }
+    __syncthreads();
     for (int b = warp; b < TB; b += VJF_NWARP) {
       float q = 0.f;
-      if (b < nb) {
-        const float* ph = phi + b * RP;
-        const float* Ug = s.U_in ? U_s : st + p.lay.w_chol;
-        for (int n = lane; n < R; n += 32) {
-          float f0 = 0.f, f1 = 0.f;
-          int r = 0;
-          for (; r + 1 < R; r += 2) { f0 = fmaf(ph[r], Ug[r * R + n], f0); f1 = fmaf(ph[r + 1], Ug[(r + 1) * R + n], f1); }
-          if (r < R) f0 = fmaf(ph[r], Ug[r * R + n], f0);
-          const float fl = f0 + f1;
-          q = fmaf(fl, fl, q);
-        }
-      }
+      for (int n = lane; n < R; n += 32) q += gxp[b * 128 + n];
       q = warp_sum(q);
       if (lane == 0) plv_s[b] = (b < nb) ? logf(q) : 0.f;
     }
@@ -413,22 +422,24 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
         for (int q = 0; q < 2; ++q)
 #pragma unroll
           for (int c = 0; c < WM_NC; ++c) { const int j = tid + VJF_NT * c; ynext[q][c] = (bb + 2 + q < nb && j < D) ? ybase[(size_t)(bb + 2 + q) * D + j] : 0.f; }
-        float xt[2][8], gx[2][8];
+        float xt[2][8], gx[2][8], onf[2];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 2; ++q) {
+          const float4 xa = *reinterpret_cast<const float4*>(xt8 + min(bb + q, TB - 1) * 8), xb = *reinterpret_cast<const float4*>(xt8 + min(bb + q, TB - 1) * 8 + 4);
+          xt[q][0] = xa.x; xt[q][1] = xa.y; xt[q][2] = xa.z; xt[q][3] = xa.w; xt[q][4] = xb.x; xt[q][5] = xb.y; xt[q][6] = xb.z; xt[q][7] = xb.w;
+          onf[q] = (bb + q < nb) ? 1.0f : 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { xt[q][k] = (k < d) ? xt_s[min(bb + q, TB - 1) * d + k] : 0.f; gx[q][k] = 0.f; }
+          for (int k = 0; k < 8; ++k) gx[q][k] = 0.f;
+        }
 #pragma unroll
         for (int c = 0; c < WM_NC; ++c) {
           const int j = tid + VJF_NT * c;
           if (j < D) {
-            float wk[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) wk[k] = (k < d) ? dec[k * D + j] : 0.f;
-            const float bj = dec[d * D + j];
+            const float4 wa = *reinterpret_cast<const float4*>(dec + j * 12), wb = *reinterpret_cast<const float4*>(dec + j * 12 + 4);
+            const float wk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float bj = dec[j * 12 + 8];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const bool on = bb + q < nb;
               float eta = bj;
 #pragma unroll
               for (int k = 0; k < 8; ++k) eta = fmaf(wk[k], xt[q][k], eta);
@@ -439,20 +450,20 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
                 const float r = yv - eta;
                 const float rsd = yv * p_lam - eta * p_lam;
                 const float mse = rsd * rsd;
-                sc[SC_BADMSE] += (on && !isfinite(mse)) ? 1.f : 0.f;
-                sc[SC_RECON] += on ? 0.5f * (mse + lam) : 0.f;
-                sc[SC_SSE] += on ? r * r : 0.f;
-                gv = -r * e_nlam;
-                sc[6] += (on && r_on) ? 0.5f * (1.0f - r * r * e_nlam) : 0.f;
+                sc[SC_BADMSE] += (onf[q] != 0.f && !isfinite(mse)) ? 1.f : 0.f;
+                sc[SC_RECON] = fmaf(onf[q], 0.5f * (mse + lam), sc[SC_RECON]);
+                sc[SC_SSE] = fmaf(onf[q] * r, r, sc[SC_SSE]);
+                gv = -r * e_nlam * onf[q];
+                sc[6] = fmaf(onf[q], 0.5f * (1.0f - r * r * e_nlam), sc[6]);
               } else {
-                // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62; NaN propagates like torch.clamp
-                const float ec = fminf(eta, 10.0f);
-                const float exv = expf(ec);
-                const bool isn = eta != eta;
-                sc[SC_RECON] += on ? (isn ? eta : exv - yv * ec) : 0.f;
-                gv = isn ? eta : ((eta <= 10.0f) ? (exv - yv) : 0.f);
+                // poisson_nll_loss(clamp(eta, max=10), y, log_input=True), likelihood.py:60-62; a NaN eta stays NaN (torch.clamp):
+                // the comparison is false for it, so it flows through exp into the loss and the gradient
+                const bool big = eta > 10.0f;
+                const float ec = big ? 10.0f : eta;
+                const float exv = __expf(ec);
+                sc[SC_RECON] = fmaf(onf[q], fmaf(-yv, ec, exv), sc[SC_RECON]);
+                gv = (big ? 0.f : exv - yv) * onf[q];
               }
-              gv = (on && r_on) ? gv : 0.f;
               acc_b[c] += gv;
 #pragma unroll
               for (int k = 0; k < 8; ++k) { acc_w[c][k] = fmaf(gv, xt[q][k], acc_w[c][k]); gx[q][k] = fmaf(gv, wk[k], gx[q][k]); }
@@ -522,7 +533,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
         if (h_on) gl -= 0.5f;
         if (d_on) { gm += (m - pm) * e_ngam; gl += 0.5f * tr; }
       }
-      gmt_s[i] = gm; glt_s[i] = gl;
+      gmt_s[i] = gm; glt_s[i] = gl; gm8[b * 8 + k] = gm; gl8[b * 8 + k] = gl;
     }
     __syncthreads();
     // ---- S7: g_pre = (g_mt W_m + g_lt W_v)(1 - h^2), kept for the small gradients and handed to the weight-gradient GEMM as
@@ -548,30 +559,73 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
     }
     __syncthreads();
     // ---- S8: the small gradients and the RLS statistics of this sub-tile into the CTA's slot ----
-    for (int i = tid; i < 2 * H * d; i += VJF_NT) {
-      const int which = i / (H * d), r = i - which * H * d, n = r / d, k = r - n * d;
-      const float* gsrc = which ? glt_s : gmt_s;
-      float a = 0.f;
-      for (int b = 0; b < nb; ++b) a = fmaf(hs[b * HP + n], gsrc[b * d + k], a);
-      wm_acc(slot + (which ? p.lay.head_v_w : p.lay.head_m_w) + r, a, first);
-    }
     if (tid < d) {
       float a = 0.f;
       for (int b = 0; b < nb; ++b) a += glt_s[b * d + tid];
       wm_acc(slot + p.lay.head_v_b + tid, a, first);
     }
-    for (int i = tid; i < (E + 1) * H; i += VJF_NT) {
-      const int e = i / H, n = i - e * H;
-      float a = 0.f;
-      if (e < E) { for (int b = 0; b < nb; ++b) a = fmaf(ex[b * E + e], gp[b * HP + n], a); }
-      else { for (int b = 0; b < nb; ++b) a += gp[b * HP + n]; }
-      wm_acc(slot + (e < E ? p.lay.mlp_w[0] + (size_t)(D + e) * H + n : p.lay.mlp_b[0] + n), a, first);
-    }
-    for (int i = tid; i < R * R; i += VJF_NT) {
-      const int r = i / R, c = i - r * R;
-      float a = 0.f;
-      for (int b = 0; b < nb; ++b) a = fmaf(phi[b * RP + r], phi[b * RP + c], a);
-      wm_acc(slot + p.pa + i, a, first);
+    {
+      // one list of register-blocked work items over all threads: phi^T phi in 4 x 2 blocks | layer-1 weight gradient rows of
+      // [u | m | l] (four inputs per item) and the bias | head weight gradients (a hidden unit x all state dimensions)
+      const int ncb = (R + 1) >> 1, nA = ((R + 3) >> 2) * ncb;
+      const int nch = EP >> 2, nW = H * (nch + 1), nHd = 2 * H;
+      for (int it = tid; it < nA + nW + nHd; it += VJF_NT) {
+        if (it < nA) {
+          const int r0 = (it / ncb) * 4, c0 = (it % ncb) * 2;
+          const int r1 = min(r0 + 1, R - 1), r2 = min(r0 + 2, R - 1), r3 = min(r0 + 3, R - 1), c1 = min(c0 + 1, R - 1);
+          float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, a20 = 0.f, a21 = 0.f, a30 = 0.f, a31 = 0.f;
+#pragma unroll 4
+          for (int b = 0; b < nb; ++b) {
+            const float* ph = phi + b * RP;
+            const float x0 = ph[r0], x1 = ph[r1], x2 = ph[r2], x3 = ph[r3], y0 = ph[c0], y1 = ph[c1];
+            a00 = fmaf(x0, y0, a00); a01 = fmaf(x0, y1, a01); a10 = fmaf(x1, y0, a10); a11 = fmaf(x1, y1, a11);
+            a20 = fmaf(x2, y0, a20); a21 = fmaf(x2, y1, a21); a30 = fmaf(x3, y0, a30); a31 = fmaf(x3, y1, a31);
+          }
+          float* o = slot + p.pa;
+          const bool c1ok = c0 + 1 < R;
+          wm_acc(o + r0 * R + c0, a00, first); if (c1ok) wm_acc(o + r0 * R + c0 + 1, a01, first);
+          if (r0 + 1 < R) { wm_acc(o + (r0 + 1) * R + c0, a10, first); if (c1ok) wm_acc(o + (r0 + 1) * R + c0 + 1, a11, first); }
+          if (r0 + 2 < R) { wm_acc(o + (r0 + 2) * R + c0, a20, first); if (c1ok) wm_acc(o + (r0 + 2) * R + c0 + 1, a21, first); }
+          if (r0 + 3 < R) { wm_acc(o + (r0 + 3) * R + c0, a30, first); if (c1ok) wm_acc(o + (r0 + 3) * R + c0 + 1, a31, first); }
+        } else if (it < nA + nW) {
+          const int i2 = it - nA, ch = i2 / H, n = i2 - ch * H;
+          if (ch < nch) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int b = 0; b < nb; ++b) {
+              const float g = gp[b * HP + n];
+              const float4 x = *reinterpret_cast<const float4*>(ex + b * EP + 4 * ch);
+              a0 = fmaf(g, x.x, a0); a1 = fmaf(g, x.y, a1); a2 = fmaf(g, x.z, a2); a3 = fmaf(g, x.w, a3);
+            }
+            float* o = slot + p.lay.mlp_w[0] + (size_t)(D + 4 * ch) * H + n;
+            if (4 * ch < E) wm_acc(o, a0, first);
+            if (4 * ch + 1 < E) wm_acc(o + H, a1, first);
+            if (4 * ch + 2 < E) wm_acc(o + 2 * H, a2, first);
+            if (4 * ch + 3 < E) wm_acc(o + 3 * H, a3, first);
+          } else {
+            float a = 0.f;
+            for (int b = 0; b < nb; ++b) a += gp[b * HP + n];
+            wm_acc(slot + p.lay.mlp_b[0] + n, a, first);
+          }
+        } else {
+          const int i2 = it - nA - nW, which = i2 / H, n = i2 - which * H;
+          const float* g8 = which ? gl8 : gm8;
+          float a[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[k] = 0.f;
+#pragma unroll 2
+          for (int b = 0; b < nb; ++b) {
+            const float h = hs[b * HP + n];
+            const float4 ga = *reinterpret_cast<const float4*>(g8 + b * 8), gb = *reinterpret_cast<const float4*>(g8 + b * 8 + 4);
+            a[0] = fmaf(h, ga.x, a[0]); a[1] = fmaf(h, ga.y, a[1]); a[2] = fmaf(h, ga.z, a[2]); a[3] = fmaf(h, ga.w, a[3]);
+            a[4] = fmaf(h, gb.x, a[4]); a[5] = fmaf(h, gb.y, a[5]); a[6] = fmaf(h, gb.z, a[6]); a[7] = fmaf(h, gb.w, a[7]);
+          }
+          float* o = slot + (which ? p.lay.head_v_w : p.lay.head_m_w) + n * d;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < d) wm_acc(o + k, a[k], first);
+        }
+      }
     }
     for (int i = tid; i < R * d; i += VJF_NT) {
       const int r = i / d, k = i - r * d;
