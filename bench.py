@@ -400,6 +400,12 @@ def time_runs(fn, reps):
     return float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
 
+def c4_tensor_flops_per_trial_step(cfg):
+    """Tensor-core FLOPs the wide-observation path issues per trial-step: the forward and the weight-gradient GEMM over the
+    observation columns, two tf32 products each (spike counts are exact in tf32; the weight / g_pre operand is a hi/lo pair)."""
+    return 2 * 2 * 2 * cfg["ydim"] * cfg["hidden"][0]
+
+
 def tensor_flops_per_trial_step(cfg):
     """Tensor-core FLOPs the tile pipeline issues per trial-step (the C2 path is tensor-bound before it is
     HBM-bound once fp32-grade accuracy is bought with hi/lo operand pairs): layer-1 forward and weight gradient over
@@ -635,10 +641,32 @@ def run_ours(args, cfg):
         ms = time_runs(step_4, 3)
         tps = B4 * T4 / (ms * 1e-3)
         ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / 1e9
+        fl4 = c4_tensor_flops_per_trial_step(c4)
         extras["c4_one_gpu_share"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {B4} trials (1/8 of 65536) x {T4} steps",
                                       "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4 * 1e3,
                                       "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
-                                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
+                                      "kernel_kind_meaning": "3 = wide-observation launch sequence (csrc/wide.cu: tcgen05 GEMMs over all trials), 0 = general persistent kernel",
+                                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                                   "note": "algorithmic bytes (SURVEY 8d); the launch sequence reads the observations three times "
+                                                           "(forward GEMM, likelihood stage, weight-gradient GEMM)"},
+                                      "tensor": {"tensor_flops_per_trial_step": fl4, "achieved_tflops": fl4 * tps / 1e12, "peak_tflops": tf32_peak,
+                                                 "frac": fl4 * tps / 1e12 / tf32_peak}}
+        del m4, y4
+        # (b2) the whole C4 batch on ONE GPU: 65536 trials per step
+        B4f, T4f = c4["global_trials"], 4
+        m4 = VJF.make_model(c4["ydim"], c4["xdim"], 0, c4["n_rbf"], c4["hidden"], c4["likelihood"], max_trials=B4f, seed=99, device=dev)
+        m4.load_full_state(bench_state(c4))
+        y4 = synthetic_counts_gpu(T4f, B4f, c4["ydim"], c4["xdim"], dev, 31)
+        st4 = m4._flat.clone()
+        ms = time_runs(step_4, 3)
+        tps = B4f * T4f / (ms * 1e-3)
+        ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / 1e9
+        extras["c4_full_batch_one_gpu"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {B4f} trials x {T4f} steps on one GPU",
+                                           "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4f * 1e3,
+                                           "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
+                                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak},
+                                           "tensor": {"tensor_flops_per_trial_step": fl4, "achieved_tflops": fl4 * tps / 1e12, "peak_tflops": tf32_peak,
+                                                      "frac": fl4 * tps / 1e12 / tf32_peak}}
         del m4, y4
     if world == 1 and not args.no_extras:
         # (c) C5, the long-horizon latency path: 1024 trials, Gaussian observations, consecutive time steps with NO state reset,
@@ -716,7 +744,7 @@ def run_ours(args, cfg):
         tps = c4["global_trials"] * T4 / (ms * 1e-3)
         ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / world / 1e9
         extras["c4_strong_scaling"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {c4['global_trials']} trials over {world} GPUs "
-                                                   f"({B4} per GPU) x {T4} steps, in-kernel NVLink all-reduce", "scaling": "strong",
+                                                   f"({B4} per GPU) x {T4} steps, " + ("wide-observation launch sequence, pull all-reduce over NVLink peer memory" if int(lib.vjf_last_launch_kind()) == 3 else "in-kernel NVLink all-reduce"), "scaling": "strong",
                                        "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4 * 1e3,
                                        "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
                                        "roofline_per_gpu": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}

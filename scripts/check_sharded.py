@@ -14,7 +14,8 @@ from vjf_b200.model import VJF
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-D, d, R, H, Bg, T = 60, 3, 20, [int(os.environ.get("CS_H", 16))], 200, 12
+# CS_D > 480 exercises the wide-observation path (csrc/wide.cu) and its pull all-reduce over peer memory
+D, d, R, H, Bg, T = int(os.environ.get("CS_D", 60)), int(os.environ.get("CS_XD", 3)), int(os.environ.get("CS_R", 20)), [int(os.environ.get("CS_H", 16))], int(os.environ.get("CS_B", 200)), int(os.environ.get("CS_T", 12))
 for lik in ("poisson", "gaussian"):
     torch.manual_seed(7)  # identical data on every rank
     y = (torch.poisson(torch.full((T, Bg, D), 0.8)) if lik == "poisson" else torch.randn(T, Bg, D)).cuda()
@@ -44,7 +45,7 @@ for lik in ("poisson", "gaussian"):
         dist.all_gather(others, flat)
         lockstep = all(torch.equal(o, others[0]) for o in others)
         st = m.status()
-        print(f"[rank {rank}] {lik}/{mode} status={st}: |mu| {e_mu:.2e} |logvar| {e_lv:.2e} loss rel {e_loss:.2e} "
+        print(f"[rank {rank}] D={D} {lik}/{mode} kind={m._lib.vjf_last_launch_kind()} status={st}: |mu| {e_mu:.2e} |logvar| {e_lv:.2e} loss rel {e_loss:.2e} "
               f"state {e_state:.2e} replicas identical: {lockstep}", flush=True)
         assert e_mu < 5e-4 and e_lv < 5e-4 and e_loss < 5e-4 and e_state < 5e-3 and lockstep and st == 0
 dist.destroy_process_group()

@@ -30,3 +30,20 @@ __global__ void __launch_bounds__(VJF_NT, 1) vjf_phase_b_kernel(const __grid_con
   }
 }
 
+
+// The two halves of phase B as separate launches (wide-observation path, wide.cu): the SGD step on every CTA, and the serial
+// part (losses, running variances, RLS: one CTA) on a side stream beside the next step's forward GEMM.
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_sgd_kernel(const __grid_constant__ StepParams p) {
+  unsigned fin = 0;
+  for (int i = 0; i < 3; ++i)
+    if (isfinite(p.reduced[p.ps + i])) fin |= 1u << i;
+  const unsigned need = base_masks(p);
+  if ((fin & need) == need) sgd_from_reduced(p, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_rls_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) float sm[];
+  unsigned fin = 0;
+  for (int i = 0; i < 3; ++i)
+    if (isfinite(p.reduced[p.ps + i])) fin |= 1u << i;
+  phase_b2(p, sm, 0, fin);
+}

@@ -34,7 +34,12 @@
 struct Wide {
   int Bmax, Bp, Dp, ZF, ZD, nslots, per;
   float *W1T, *W1Tlo, *pre, *GT, *GTlo, *dWT, *ylo;
+  cudaStream_t side; cudaEvent_t ev_sgd, ev_rls;  // host side: the serial half of phase B runs beside the next step's forward GEMM
 };
+
+// the two halves of phase B as separate launches (k_split.cu)
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_sgd_kernel(const __grid_constant__ StepParams p);
+__global__ void __launch_bounds__(VJF_NT, 1) vjf_rls_kernel(const __grid_constant__ StepParams p);
 
 namespace wg {
 constexpr int BM = 128, BN = 128;
@@ -680,21 +685,31 @@ __global__ void wide_reduce_w1_kernel(const StepParams p, const Wide w, float* _
   }
 }
 
-// everything else of the reduced vector: sums over the mid kernel's slots in slot order
+// everything else of the reduced vector: sums over the mid kernel's slots.  A block owns 32 consecutive elements; warp w adds
+// the slots w, w + 8, ... (independent 128-byte row loads in flight together), the eight partial sums meet in a fixed order
 __global__ void __launch_bounds__(256) wide_reduce_rest_kernel(const StepParams p, const Wide w, float* __restrict__ out) {
+  __shared__ float part[8][32];
   const int w0 = p.lay.mlp_w[0], w1 = w0 + p.D * p.H[0];  // the y-rows of dW1 come from the GEMM
   const int n_rest = p.PS - (w1 - w0);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rest) return;
-  const int e = (i < w0) ? i : i + (w1 - w0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int ic = min(i, n_rest - 1);
+  const int e = (ic < w0) ? ic : ic + (w1 - w0);
   const float* src = p.partials + e;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int c = 0;
-  for (; c + 3 < w.nslots; c += 4) {
-    a0 += src[(size_t)c * p.PS]; a1 += src[(size_t)(c + 1) * p.PS]; a2 += src[(size_t)(c + 2) * p.PS]; a3 += src[(size_t)(c + 3) * p.PS];
+  int c = warp;
+  for (; c + 24 < w.nslots; c += 32) {
+    a0 += src[(size_t)c * p.PS]; a1 += src[(size_t)(c + 8) * p.PS]; a2 += src[(size_t)(c + 16) * p.PS]; a3 += src[(size_t)(c + 24) * p.PS];
   }
-  for (; c < w.nslots; ++c) a0 += src[(size_t)c * p.PS];
-  out[e] = (a0 + a1) + (a2 + a3);
+  for (; c < w.nslots; c += 8) a0 += src[(size_t)c * p.PS];
+  part[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0 && i < n_rest) {
+    float t = part[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += part[k][lane];
+    out[e] = t;
+  }
 }
 
 // Sharded run: pull all-reduce of the reduced vector over NVLink peer memory.  Every rank's local sums sit in its own
@@ -789,6 +804,10 @@ int vjf_wide_create(vjf_handle* h) {
   bad |= alloc(&w->GT, H * (size_t)w->Bp); bad |= alloc(&w->GTlo, H * (size_t)w->Bp); bad |= alloc(&w->dWT, (size_t)ZDmax * H * w->Dp);
   if (bad) { vjf_set_error("ydim=%d, max_trials=%d: out of device memory for the wide-observation workspace", p.D, h->cfg.max_trials); free(w); return -2; }
   h->wide = w;
+  VJF_CUDA_OK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+  VJF_CUDA_OK(cudaEventCreateWithFlags(&w->ev_sgd, cudaEventDisableTiming));
+  VJF_CUDA_OK(cudaEventCreateWithFlags(&w->ev_rls, cudaEventDisableTiming));
+  VJF_CUDA_OK(cudaFuncSetAttribute(vjf_rls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   VJF_CUDA_OK(cudaFuncSetAttribute(wide_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024 + 256 + 1024)));
   VJF_CUDA_OK(cudaFuncSetAttribute(wide_mid_kernel<VJF_LIK_POISSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
   VJF_CUDA_OK(cudaFuncSetAttribute(wide_mid_kernel<VJF_LIK_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit));
@@ -798,6 +817,9 @@ int vjf_wide_create(vjf_handle* h) {
 void vjf_wide_destroy(vjf_handle* h) {
   Wide* w = h->wide;
   if (!w) return;
+  if (w->side) cudaStreamDestroy(w->side);
+  if (w->ev_sgd) cudaEventDestroy(w->ev_sgd);
+  if (w->ev_rls) cudaEventDestroy(w->ev_rls);
   cudaFree(w->W1T); cudaFree(w->W1Tlo); cudaFree(w->pre); cudaFree(w->GT); cudaFree(w->GTlo); cudaFree(w->dWT); cudaFree(w->ylo);
   free(w);
   h->wide = nullptr;
@@ -855,6 +877,8 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
       wmap2d(&mG, w.GT, H, B, w.Bp, wg::BM, false) || wmap2d(&mGlo, w.GTlo, H, B, w.Bp, wg::BM, false)) return -2;
   const size_t PSx = (size_t)((pl.PS + 127) & ~127);
   const int nb_grid = std::max(1, std::min(h->num_sms, (pl.lay.n_train + VJF_NT - 1) / VJF_NT));
+  static const bool no_overlap = getenv("VJF_WIDE_NO_OVERLAP") != nullptr;
+  const bool overlap = !no_overlap && !tm.on;
   for (int t = 0; t < T; ++t) {
     StepParams p = pl;
     const float* yt = reinterpret_cast<const float*>(pl.y) + (size_t)t * B * D;
@@ -882,6 +906,7 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
       wide_gemm_kernel<<<dim3(mt, 1, w.ZF), wg::NT, smem_f, s>>>(mYk, mYlok, mW, mWlo, g);
     }
     tm.mark("mid");
+    if (t > 0 && overlap) VJF_CUDA_OK(cudaStreamWaitEvent(s, w.ev_rls, 0));  // w_mean / w_chol / noise variances of step t-1
     if (pl.lik == VJF_LIK_GAUSSIAN) wide_mid_kernel<VJF_LIK_GAUSSIAN><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm);
     else wide_mid_kernel<VJF_LIK_POISSON><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm);
     tm.mark("gemm_dw");
@@ -894,14 +919,24 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     const unsigned epoch = pl.epoch0 + (unsigned)t + 1;
     float* red_out = (pl.world > 1) ? pl.peer[pl.rank] + ((size_t)pl.rank * 2 + (epoch & 1)) * PSx : p.reduced;
     wide_reduce_w1_kernel<<<dim3((D + 31) / 32, (H + 31) / 32), dim3(32, 8), 0, s>>>(p, w, red_out);
-    wide_reduce_rest_kernel<<<(pl.PS - D * H + 255) / 256, 256, 0, s>>>(p, w, red_out);
+    wide_reduce_rest_kernel<<<(pl.PS - D * H + 31) / 32, 256, 0, s>>>(p, w, red_out);
     if (pl.world > 1) {
       tm.mark("exchange");
       wide_exchange_kernel<<<std::min(h->num_sms, (pl.PS / 4 + 255) / 256), 256, 0, s>>>(p, epoch);
       ++g_vjf_launches;
     }
     tm.mark("phase_b");
-    vjf_phase_b_kernel<<<nb_grid, VJF_NT, (size_t)p.s_total * sizeof(float), s>>>(p);
+    if (overlap) {
+      vjf_sgd_kernel<<<nb_grid, VJF_NT, 0, s>>>(p);
+      VJF_CUDA_OK(cudaEventRecord(w.ev_sgd, s));
+      VJF_CUDA_OK(cudaStreamWaitEvent(w.side, w.ev_sgd, 0));
+      vjf_rls_kernel<<<1, VJF_NT, (size_t)p.s_total * sizeof(float), w.side>>>(p);
+      VJF_CUDA_OK(cudaEventRecord(w.ev_rls, w.side));
+      if (t == T - 1) VJF_CUDA_OK(cudaStreamWaitEvent(s, w.ev_rls, 0));
+      ++g_vjf_launches;
+    } else {
+      vjf_phase_b_kernel<<<nb_grid, VJF_NT, (size_t)p.s_total * sizeof(float), s>>>(p);
+    }
     g_vjf_launches += 7;
     tm.mark("end");
   }
