@@ -418,15 +418,15 @@ def tensor_flops_per_trial_step(cfg):
     return 3 * 2 * (2 * K1 * H + Rk * NQ + NQ * NQ)
 
 
-def sharded_parity_check(dev, world, rank, seed=5):
-    """Short sharded run (C2 shapes, 192 trials per rank, 4 steps, noise tape) against the fp64 oracle of the WHOLE batch on
-    rank 0, and bitwise identity of the replicas: SCALE lines carry the evidence that the multi-GPU path computes the same
-    thing (the driver's GPU tests run on one GPU only)."""
+def sharded_parity_check(dev, world, rank, seed=5, cfg=None, Bl=192, T=4):
+    """Short sharded run (C2 shapes by default, 192 trials per rank, 4 steps, noise tape) against the fp64 oracle of the WHOLE
+    batch on rank 0, and bitwise identity of the replicas: SCALE lines carry the evidence that the multi-GPU path computes the
+    same thing (the driver's GPU tests run on one GPU only).  With cfg = C4 the wide-observation path and its pull all-reduce."""
     import torch
     import torch.distributed as dist
     from vjf_b200.model import VJF
     from vjf_b200.distributed import ShardedVJF
-    cfg, Bl, T = C2, 192, 4
+    cfg = cfg or C2
     D, d = cfg["ydim"], cfg["xdim"]
     Bg = Bl * world
     rng = np.random.default_rng(seed)
@@ -451,7 +451,8 @@ def sharded_parity_check(dev, world, rank, seed=5):
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     mus = [torch.empty_like(mu) for _ in range(world)]
     dist.all_gather(mus, mu.contiguous())
-    out = {"trials_per_rank": Bl, "time_steps": T, "replicas_identical": bool(same.item()), "status_word": int(status)}
+    out = {"trials_per_rank": Bl, "time_steps": T, "replicas_identical": bool(same.item()), "status_word": int(status),
+           "kernel_kind": int(m._lib.vjf_last_launch_kind())}
     if rank == 0:
         from oracle.vjf_oracle import OracleVJF
         o = OracleVJF(D, d, 0, cfg["n_rbf"], cfg["hidden"], cfg["likelihood"], lr=1e-3, dtype=np.float64)
@@ -749,6 +750,7 @@ def run_ours(args, cfg):
                                        "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
                                        "roofline_per_gpu": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}
         del r4, m4, y4
+        extras["c4_strong_scaling"]["parity_check"] = sharded_parity_check(dev, world, rank, seed=6, cfg=c4, Bl=96, T=3)
 
     if world > 1:
         tt = torch.tensor([total_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)

@@ -179,6 +179,14 @@ int vjf_set_rls_precision(vjf_handle* h, int32_t bits);
  * and profiling: 0 phi [B][n_rbf], 1 p_mean [B][xdim], 2 p_logvar [B], 3 split-K partial sums of phi^T phi; NULL otherwise. */
 float* vjf_bigr_buffer(vjf_handle* h, int32_t which);
 
+/* Wide observations (ydim above the tile pipeline's 480 columns, up to 2048; BASELINE config 4: ydim 2000, xdim 8): one hidden
+ * layer of <= 128 units, xdim <= 8, n_rbf <= 128, fp32 observations run a per-step launch sequence under the same entry points
+ * (vjf_step / vjf_run / vjf_run_host / vjf_run_sharded): the two contractions over the observation columns (recognition layer-1
+ * forward, vjf/recognition.py:38, and its weight gradient) as tcgen05 GEMMs over all trials of the step, one trial-parallel kernel
+ * for the rest, the serial RLS half of the step on a side stream beside the next step's forward GEMM (csrc/wide.cu);
+ * vjf_last_launch_kind() reports 3.  Sharded: the reduced vector is summed by a pull all-reduce over the peer-mapped exchange
+ * buffers of vjf_comm_connect.  A non-finite ELBO term skips the SGD step (the split path's rule, vjf/model.py:212-214). */
+
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);
 
@@ -191,10 +199,11 @@ int vjf_philox_normal(uint64_t seed, uint64_t step_index, uint64_t trial_offset,
 int64_t vjf_launch_count(void);
 /* which kernel ran the most recent vjf_run / vjf_step / vjf_run_sharded time loop: 1 = throughput tile pipeline (every
  * contraction on tcgen05, observations by TMA tensor copies), 0 = the general persistent kernel (shapes outside the tile plan:
- * several hidden layers, hidden width not a multiple of 32, uint8 observations, ...) */
+ * several hidden layers, hidden width not a multiple of 32, uint8 observations, ...), 2 = large-n_rbf launch sequence, 3 = wide-
+ * observation launch sequence */
 int32_t vjf_last_launch_kind(void);
 /* kernel selection of the time loop (process-wide; for tests and A/B timing): 0 automatic (default), 1 general persistent kernel
- * only, 2 tile pipeline without its exact-observation mode, 3 tile pipeline with 64-trial tiles whenever the observations are
+ * only (no tile pipeline, no wide-observation path), 2 tile pipeline without its exact-observation mode, 3 tile pipeline with 64-trial tiles whenever the observations are
  * exact in tf32 (spike counts) */
 int vjf_set_tile_mode(int32_t mode);
 

@@ -34,6 +34,8 @@
 struct Wide {
   int Bmax, Bp, Dp, ZF, ZD, nslots, per;
   float *W1T, *W1Tlo, *pre, *GT, *GTlo, *dWT, *ylo;
+  unsigned long long* stamps;     // development aid (VJF_WIDE_STAMPS=1): globaltimer stamps of the last step, see scripts/c4_time.py
+  unsigned* flag; unsigned seq;   // completion counter of the side-stream RLS launches (device word, host copy)
   cudaStream_t side; cudaEvent_t ev_sgd, ev_rls;  // host side: the serial half of phase B runs beside the next step's forward GEMM
 };
 
@@ -51,6 +53,7 @@ struct Args {
   int M, N, K;       // C (M x N) = A (M x K) B^T
   int b_mn;          // B is read MN-major from a [K][N] row-major matrix (boxes of 32 columns x 32 rows, ATOM_32B swizzle)
   int has_alo, has_blo;
+  int dual;          // 0: one 128 x 128 tile; 1: two row tiles (two A images share a B image); 2: two column tiles (two B images share A)
   int stages;
   float* out;        // out[z][row][col], row stride ldo
   int ldo;
@@ -85,11 +88,11 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   using namespace wg;
   extern __shared__ unsigned char smraw[];
   unsigned char* sb = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-  const int nimg = 2 + g.has_alo + g.has_blo, stage_bytes = nimg * IMG, ST = g.stages;
+  const int nimg = 2 + g.has_alo + g.has_blo + (g.dual == 1 ? 1 + g.has_alo : (g.dual == 2 ? 1 + g.has_blo : 0)), stage_bytes = nimg * IMG, ST = g.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + ST * stage_bytes);  // full[ST] empty[ST] accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * BM * (g.dual == 1 ? 2 : 1), n0 = blockIdx.y * BN * (g.dual == 2 ? 2 : 1);
   const int NK = (g.K + 31) >> 5;
   const int per = (NK + gridDim.z - 1) / gridDim.z;
   const int kc0 = blockIdx.z * per, nk = max(0, min(NK, kc0 + per) - kc0);
@@ -103,8 +106,9 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // image order inside a stage: A | B | A lo | B lo
+  // image order inside a stage: A | B | A lo | B lo | second tile: its A (| A lo) or its B (| B lo)
   const int o_b = IMG, o_alo = 2 * IMG, o_blo = (2 + g.has_alo) * IMG;
+  const int o_2 = (2 + g.has_alo + g.has_blo) * IMG, o_2lo = o_2 + IMG, ntile = g.dual ? 2 : 1;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -116,15 +120,22 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_expect_tx(bars + s, (uint32_t)stage_bytes);
         tensor2d(st, &mapA, k, m0, bars + s);
         if (g.has_alo) tensor2d(st + o_alo, &mapAlo, k, m0, bars + s);
-        if (g.b_mn) {
+        if (g.dual == 1) {
+          tensor2d(st + o_2, &mapA, k, m0 + BM, bars + s);
+          if (g.has_alo) tensor2d(st + o_2lo, &mapAlo, k, m0 + BM, bars + s);
+        }
+        for (int tl = 0; tl < (g.dual == 2 ? 2 : 1); ++tl) {
+          const int nn = n0 + tl * BN, ob = tl ? o_2 : o_b, obl = tl ? o_2lo : o_blo;
+          if (g.b_mn) {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            tensor2d(st + o_b + c * 4096, &mapB, n0 + 32 * c, k, bars + s);
-            if (g.has_blo) tensor2d(st + o_blo + c * 4096, &mapBlo, n0 + 32 * c, k, bars + s);
+            for (int c = 0; c < BN / 32; ++c) {
+              tensor2d(st + ob + c * 4096, &mapB, nn + 32 * c, k, bars + s);
+              if (g.has_blo) tensor2d(st + obl + c * 4096, &mapBlo, nn + 32 * c, k, bars + s);
+            }
+          } else {
+            tensor2d(st + ob, &mapB, k, nn, bars + s);
+            if (g.has_blo) tensor2d(st + obl, &mapBlo, k, nn, bars + s);
           }
-        } else {
-          tensor2d(st + o_b, &mapB, k, n0, bars + s);
-          if (g.has_blo) tensor2d(st + o_blo, &mapBlo, k, n0, bars + s);
         }
       }
     }
@@ -136,14 +147,18 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       tc_fence_after();
       if (lane == 0) {
         const uint32_t base = smem_u32(sb + s * stage_bytes);
-        const uint32_t a_hi = base, b_hi = base + o_b, a_lo = base + o_alo, b_lo = base + o_blo;
+        for (int tl = 0; tl < ntile; ++tl) {
+          const uint32_t a_hi = base + ((tl && g.dual == 1) ? o_2 : 0), a_lo = base + ((tl && g.dual == 1) ? o_2lo : o_alo);
+          const uint32_t b_hi = base + ((tl && g.dual == 2) ? o_2 : o_b), b_lo = base + ((tl && g.dual == 2) ? o_2lo : o_blo);
+          const uint32_t dcol = tmem + tl * BN;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // four k-steps of 8: +32 bytes inside the K-major 128-byte rows, +8 rows of the MN-major image
-          const uint32_t oa = j * 32, ob = g.b_mn ? j * 1024 : j * 32;
-          uint32_t acc = (i > 0 || j > 0) ? 1u : 0u;
-          if (g.has_alo) { umma_tf32_ss(tmem, kmaj(a_lo + oa), g.b_mn ? mnmaj(b_hi + ob) : kmaj(b_hi + ob), id, acc); acc = 1u; }
-          if (g.has_blo) { umma_tf32_ss(tmem, kmaj(a_hi + oa), g.b_mn ? mnmaj(b_lo + ob) : kmaj(b_lo + ob), id, acc); acc = 1u; }
-          umma_tf32_ss(tmem, kmaj(a_hi + oa), g.b_mn ? mnmaj(b_hi + ob) : kmaj(b_hi + ob), id, acc);
+          for (int j = 0; j < 4; ++j) {  // four k-steps of 8: +32 bytes inside the K-major 128-byte rows, +8 rows of the MN-major image
+            const uint32_t oa = j * 32, ob = g.b_mn ? j * 1024 : j * 32;
+            uint32_t acc = (i > 0 || j > 0) ? 1u : 0u;
+            if (g.has_alo) { umma_tf32_ss(dcol, kmaj(a_lo + oa), g.b_mn ? mnmaj(b_hi + ob) : kmaj(b_hi + ob), id, acc); acc = 1u; }
+            if (g.has_blo) { umma_tf32_ss(dcol, kmaj(a_hi + oa), g.b_mn ? mnmaj(b_lo + ob) : kmaj(b_lo + ob), id, acc); acc = 1u; }
+            umma_tf32_ss(dcol, kmaj(a_hi + oa), g.b_mn ? mnmaj(b_hi + ob) : kmaj(b_hi + ob), id, acc);
+          }
         }
         umma_commit(bars + MAXST + s);
         if (i == nk - 1) umma_commit(bars + 2 * MAXST);
@@ -154,11 +169,12 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // ---- epilogue: warp w reaches the tensor-memory lanes of quarter w % 4 ----
     if (nk > 0) { wait(bars + 2 * MAXST, 0); tc_fence_after(); }
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    for (int tl = 0; tl < ntile; ++tl)
     for (int cb = 0; cb < BN / 32; ++cb) {
-      const int col0 = cb * 32;
+      const int row = m0 + (g.dual == 1 ? tl * BM : 0) + q * 32 + lane;
+      const int col0 = (g.dual == 2 ? tl * BN : 0) + cb * 32;
       float v[32];
-      if (nk > 0) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + col0, v);
+      if (nk > 0) tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tl * BN + cb * 32, v);
       else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -242,7 +258,7 @@ static inline WideSm wide_plan(const StepParams& p, bool u_in) {
 __device__ __forceinline__ void wm_acc(float* p, float v, bool first) { *p = first ? v : *p + v; }  // a CTA's slot is its own
 
 template <int LIK>
-__global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p, const Wide w, const WideSm s) {
+__global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p, const Wide w, const WideSm s, const unsigned wait_seq) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, u = p.u, R = p.R, du = p.du, E = p.E, H = p.H[0], HP = s.HP, RP = s.RP, EP = s.EP, B = p.B;
@@ -258,24 +274,47 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
   const bool r_on = true, d_on = !(p.flags & VJF_FLAG_WARMUP), h_on = true;
 
   // ---- parameters of this step into shared memory ----
-  if (s.U_in) for (int i = tid; i < R * R; i += VJF_NT) U_s[i] = st[p.lay.w_chol + i];
-  for (int i = tid; i < R * d; i += VJF_NT) Wm[i] = st[p.lay.w_mean + i];
   for (int i = tid; i < R * du; i += VJF_NT) cen[i] = st[p.lay.centroid + i];
   for (int i = tid; i < R; i += VJF_NT) { const float wd = expf(st[p.lay.logwidth + i]); iw[i] = -0.5f / (wd * wd); }
   for (int i = tid; i < E * H; i += VJF_NT) W1e[i] = st[p.lay.mlp_w[0] + (size_t)D * H + i];
   for (int i = tid; i < H; i += VJF_NT) W1e[E * H + i] = st[p.lay.mlp_b[0] + i];
   for (int i = tid; i < H * d; i += VJF_NT) { hm[i] = st[p.lay.head_m_w + i]; hv[i] = st[p.lay.head_v_w + i]; }
   for (int i = tid; i < d; i += VJF_NT) hv[H * d + i] = st[p.lay.head_v_b + i];
-  for (int i = tid; i < 8 * D; i += VJF_NT) { const int k = i / D, j = i - k * D; dec[j * 12 + k] = (k < d) ? st[p.lay.dec_w + i] : 0.f; }
+  for (int k = 0; k < 8; ++k)
+    for (int j = tid; j < D; j += VJF_NT) dec[j * 12 + k] = (k < d) ? st[p.lay.dec_w + k * D + j] : 0.f;
   for (int i = tid; i < D; i += VJF_NT) dec[i * 12 + 8] = st[p.lay.dec_b + i];
   for (int i = tid; i < TB * 8; i += VJF_NT) { xt8[i] = 0.f; gm8[i] = 0.f; gl8[i] = 0.f; }
   for (int i = tid; i < TB * EP; i += VJF_NT) ex[i] = 0.f;
-  float lam = 0.f;
-  if (LIK == VJF_LIK_GAUSSIAN) lam = st[p.lay.lik_logvar];
-  const float e_nlam = expf(-lam), p_lam = expf(-0.5f * lam);
-  const float gam = st[p.lay.tr_logvar];
-  const float e_ngam = expf(-gam), p_gam = expf(-0.5f * gam);
+  // What the serial half of the previous step (vjf_rls_kernel, side stream) writes -- w_chol, w_mean, the noise variances -- is
+  // read only after its completion counter has reached wait_seq: with spike counts (no observation-noise parameter) that is
+  // after the likelihood stage of the first sub-tile, so the RLS hides behind the forward GEMM and most of this kernel's work.
+  // The grid leaves one SM free (host), so the RLS launch can always be scheduled; a lost launch times out instead of hanging.
+  if (w.stamps && blockIdx.x == 0 && tid == 0) w.stamps[(p.step0 & 7) * 8 + 2] = (unsigned long long)gtime_ns();
+  bool rls_ready = false;
+  float lam = 0.f, e_nlam = 1.f, p_lam = 1.f, gam = 0.f, e_ngam = 1.f, p_gam = 1.f;
+  auto wait_rls = [&]() {
+    if (w.stamps && blockIdx.x == 0 && tid == 0) w.stamps[(p.step0 & 7) * 8 + 3] = (unsigned long long)gtime_ns();
+    if (tid == 0 && wait_seq) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(w.flag) < wait_seq) {
+        if (clock64() - t0 > 4000000000ll) { atomicOr(p.status, (unsigned)VJF_ST_COMM_TIMEOUT); break; }
+        __nanosleep(64);
+      }
+      __threadfence();
+    }
+    if (w.stamps && blockIdx.x == 0 && tid == 0) w.stamps[(p.step0 & 7) * 8 + 4] = (unsigned long long)gtime_ns();
+    __syncthreads();
+    if (s.U_in) for (int i = tid; i < R * R; i += VJF_NT) U_s[i] = __ldcg(st + p.lay.w_chol + i);
+    for (int i = tid; i < R * d; i += VJF_NT) Wm[i] = __ldcg(st + p.lay.w_mean + i);
+    if (LIK == VJF_LIK_GAUSSIAN) lam = __ldcg(st + p.lay.lik_logvar);
+    e_nlam = expf(-lam); p_lam = expf(-0.5f * lam);
+    gam = __ldcg(st + p.lay.tr_logvar);
+    e_ngam = expf(-gam); p_gam = expf(-0.5f * gam);
+    rls_ready = true;
+    __syncthreads();
+  };
   __syncthreads();
+  if (LIK == VJF_LIK_GAUSSIAN) wait_rls();  // the decoder stage needs the observation-noise variance of the previous step
 
   float acc_w[WM_NC][8], acc_b[WM_NC], sc[VJF_NSCAL];
 #pragma unroll
@@ -373,43 +412,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
         mt_s[bk] = m; lt_s[bk] = lv; xt_s[bk] = x; dx_s[bk] = dxv; xt8[b * 8 + k] = x;
       }
     }
-    // ---- S4: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W, p_logvar = log |phi w_chol|^2 ----
-    {  // FL[b][n] = sum_r phi[b][r] w_chol[r][n]: a thread owns one column n for four trials (one load of w_chol per four FMAs)
-      const float* Ug = s.U_in ? U_s : st + p.lay.w_chol;
-      for (int it = tid; it < R * (TB / 4); it += VJF_NT) {
-        const int bg = it / R, n = it - bg * R;
-        const float* ph = phi + (4 * bg) * RP;
-        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll 4
-        for (int r = 0; r < R; ++r) {
-          const float uv = Ug[r * R + n];
-          f0 = fmaf(ph[r], uv, f0); f1 = fmaf(ph[RP + r], uv, f1); f2 = fmaf(ph[2 * RP + r], uv, f2); f3 = fmaf(ph[3 * RP + r], uv, f3);
-        }
-        float* o = gxp + (4 * bg) * 128 + n;  // (scratch: the g_xt partial sums are not live yet)
-        o[0] = f0 * f0; o[128] = f1 * f1; o[256] = f2 * f2; o[384] = f3 * f3;
-      }
-    }
-    __syncthreads();
-    for (int b = warp; b < TB; b += VJF_NWARP) {
-      float q = 0.f;
-      for (int n = lane; n < R; n += 32) q += gxp[b * 128 + n];
-      q = warp_sum(q);
-      if (lane == 0) plv_s[b] = (b < nb) ? logf(q) : 0.f;
-    }
-    __syncthreads();  // (xt_s, mt_s ... of S3 visible)
-    for (int i = tid; i < TB * d; i += VJF_NT) {
-      const int b = i / d, k = i - b * d;
-      float a = 0.f;
-      if (b < nb) {
-        const float* ph = phi + b * RP;
-        float a0 = 0.f, a1 = 0.f;
-        int r = 0;
-        for (; r + 1 < R; r += 2) { a0 = fmaf(ph[r], Wm[r * d + k], a0); a1 = fmaf(ph[r + 1], Wm[(r + 1) * d + k], a1); }
-        if (r < R) a0 = fmaf(ph[r], Wm[r * d + k], a0);
-        a = xu[b * du + k] + (a0 + a1);
-      }
-      pm_s[i] = a;
-    }
+    __syncthreads();  // (xt8, mt_s ... of S3 visible)
     // ---- S5: decoder eta = D xt + bias (model.py:29-30), likelihood, d loss / d eta (times B), decoder gradients, g_xt.
     //      A thread owns the observation columns tid + 512 c and keeps their decoder gradients in registers across all of the
     //      CTA's trials; two trials are in flight, their g_xt partial sums (16 values) meet in one transposed warp reduction ----
@@ -518,14 +521,58 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
       }
     }
     __syncthreads();
+    for (int i = tid; i < TB * d; i += VJF_NT) {  // g_xt: the warps' partial sums in warp order
+      const int b = i / d, k = i - b * d;
+      float gxv = 0.f;
+      for (int wv = 0; wv < VJF_NWARP; ++wv) gxv += gxp[(wv * TB + b) * 8 + k];
+      gxt_s[i] = gxv;
+    }
+    if (!rls_ready) wait_rls();  // (first sub-tile: the RLS outputs of the previous step)
+    else __syncthreads();
+    // ---- S4: dynamics read-out (vjf/module.py:75-77, model.py:338): p_mean = xs + phi W, p_logvar = log |phi w_chol|^2 ----
+    {  // FL[b][n] = sum_r phi[b][r] w_chol[r][n]: a thread owns one column n for four trials (one load of w_chol per four FMAs)
+      const float* Ug = s.U_in ? U_s : st + p.lay.w_chol;
+      for (int it = tid; it < R * (TB / 4); it += VJF_NT) {
+        const int bg = it / R, n = it - bg * R;
+        const float* ph = phi + (4 * bg) * RP;
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll 4
+        for (int r = 0; r < R; ++r) {
+          const float uv = Ug[r * R + n];
+          f0 = fmaf(ph[r], uv, f0); f1 = fmaf(ph[RP + r], uv, f1); f2 = fmaf(ph[2 * RP + r], uv, f2); f3 = fmaf(ph[3 * RP + r], uv, f3);
+        }
+        float* o = gxp + (4 * bg) * 128 + n;  // (scratch: the g_xt partial sums are not live yet)
+        o[0] = f0 * f0; o[128] = f1 * f1; o[256] = f2 * f2; o[384] = f3 * f3;
+      }
+    }
+    __syncthreads();
+    for (int b = warp; b < TB; b += VJF_NWARP) {
+      float q = 0.f;
+      for (int n = lane; n < R; n += 32) q += gxp[b * 128 + n];
+      q = warp_sum(q);
+      if (lane == 0) plv_s[b] = (b < nb) ? logf(q) : 0.f;
+    }
+    __syncthreads();  // (xt_s, mt_s ... of S3 visible)
+    for (int i = tid; i < TB * d; i += VJF_NT) {
+      const int b = i / d, k = i - b * d;
+      float a = 0.f;
+      if (b < nb) {
+        const float* ph = phi + b * RP;
+        float a0 = 0.f, a1 = 0.f;
+        int r = 0;
+        for (; r + 1 < R; r += 2) { a0 = fmaf(ph[r], Wm[r * d + k], a0); a1 = fmaf(ph[r + 1], Wm[(r + 1) * d + k], a1); }
+        if (r < R) a0 = fmaf(ph[r], Wm[r * d + k], a0);
+        a = xu[b * du + k] + (a0 + a1);
+      }
+      pm_s[i] = a;
+    }
+    __syncthreads();
     // ---- S6: dynamics NLL (functional.py:55-75 via model.py:390-391), entropy (functional.py:25-29), g_mt and g_lt (times B) ----
     for (int i = tid; i < TB * d; i += VJF_NT) {
       const int b = i / d, k = i - b * d;
       float gm = 0.f, gl = 0.f;
       if (b < nb) {
-        float gxv = 0.f;
-        for (int wv = 0; wv < VJF_NWARP; ++wv) gxv += gxp[(wv * TB + b) * 8 + k];
-        gxt_s[i] = gxv;
+        const float gxv = gxt_s[i];
         const float m = mt_s[i], lv = lt_s[i], pm = pm_s[i], plv = plv_s[b];
         const float e2 = eps_s[b * 2 * d + d + k];
         const float df = pm * p_gam - m * p_gam;
@@ -642,6 +689,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
     __syncthreads();
   }
 
+  if (w.stamps && blockIdx.x == 0 && tid == 0) w.stamps[(p.step0 & 7) * 8 + 5] = (unsigned long long)gtime_ns();
   // ---- flush: decoder gradients (registers) and the scalar sums ----
 #pragma unroll
   for (int c = 0; c < WM_NC; ++c) {
@@ -666,6 +714,14 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
     else slot[p.ps + tid] = v;
   }
 }
+
+// completion counter of the side-stream launches (the kernel boundary orders the RLS kernel's stores before it)
+__global__ void wide_flag_kernel(unsigned* flag, unsigned value, unsigned long long* stamp) {
+  if (stamp) *stamp = (unsigned long long)gtime_ns();
+  __threadfence();
+  st_release_gpu_u32(flag, value);
+}
+__global__ void wide_stamp_kernel(unsigned long long* stamp) { *stamp = (unsigned long long)gtime_ns(); }
 
 // reduced[y-rows of dW1][j][n] = sum_z dWT[z][n][j]  (transposing, fixed order)
 __global__ void wide_reduce_w1_kernel(const StepParams p, const Wide w, float* __restrict__ out) {
@@ -797,13 +853,16 @@ int vjf_wide_create(vjf_handle* h) {
   w->Bmax = (int)B;
   w->Bp = (int)((B + 3) & ~(size_t)3); if ((w->Bp * 4) % 4096 == 0) w->Bp += 32;
   w->Dp = (int)((D + 3) & ~(size_t)3); if ((w->Dp * 4) % 4096 == 0) w->Dp += 32;
-  const int ZFmax = 4, ZDmax = 16;
+  const int ZFmax = 4, ZDmax = 20;
   auto alloc = [&](float** ptr, size_t n) { if (cudaMalloc(ptr, n * sizeof(float)) != cudaSuccess) return -1; return cudaMemset(*ptr, 0, n * sizeof(float)) == cudaSuccess ? 0 : -1; };
   int bad = 0;
   bad |= alloc(&w->W1T, H * w->Dp); bad |= alloc(&w->W1Tlo, H * w->Dp); bad |= alloc(&w->pre, (size_t)ZFmax * B * H);
   bad |= alloc(&w->GT, H * (size_t)w->Bp); bad |= alloc(&w->GTlo, H * (size_t)w->Bp); bad |= alloc(&w->dWT, (size_t)ZDmax * H * w->Dp);
   if (bad) { vjf_set_error("ydim=%d, max_trials=%d: out of device memory for the wide-observation workspace", p.D, h->cfg.max_trials); free(w); return -2; }
   h->wide = w;
+  VJF_CUDA_OK(cudaMalloc(&w->flag, 1024));
+  VJF_CUDA_OK(cudaMemset(w->flag, 0, 1024));
+  if (getenv("VJF_WIDE_STAMPS")) w->stamps = reinterpret_cast<unsigned long long*>(w->flag + 64);
   VJF_CUDA_OK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
   VJF_CUDA_OK(cudaEventCreateWithFlags(&w->ev_sgd, cudaEventDisableTiming));
   VJF_CUDA_OK(cudaEventCreateWithFlags(&w->ev_rls, cudaEventDisableTiming));
@@ -820,7 +879,7 @@ void vjf_wide_destroy(vjf_handle* h) {
   if (w->side) cudaStreamDestroy(w->side);
   if (w->ev_sgd) cudaEventDestroy(w->ev_sgd);
   if (w->ev_rls) cudaEventDestroy(w->ev_rls);
-  cudaFree(w->W1T); cudaFree(w->W1Tlo); cudaFree(w->pre); cudaFree(w->GT); cudaFree(w->GTlo); cudaFree(w->dWT); cudaFree(w->ylo);
+  cudaFree(w->flag); cudaFree(w->W1T); cudaFree(w->W1Tlo); cudaFree(w->pre); cudaFree(w->GT); cudaFree(w->GTlo); cudaFree(w->dWT); cudaFree(w->ylo);
   free(w);
   h->wide = nullptr;
 }
@@ -862,16 +921,22 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
   WideSm sm = wide_plan(pl, true);
   if ((size_t)sm.total * 4 > h->smem_limit) sm = wide_plan(pl, false);
   // trials per CTA of the mid kernel: balanced, a multiple of 4; every CTA has work
-  const int G0 = std::min(h->max_slots, (B + 3) / 4);
+  const int G0 = std::min(h->max_slots - 1, (B + 3) / 4);  // one SM stays free for the side-stream RLS launch (see wide_mid_kernel)
   w.per = (((B + G0 - 1) / G0) + 3) & ~3;
   w.nslots = (B + w.per - 1) / w.per;
   // split-K factors: fill the SMs
-  const int mt = (B + wg::BM - 1) / wg::BM, nkf = (D + 31) / 32;
+  // two output tiles per CTA share the weight / g_pre images of a stage (fewer bytes from L2 per tensor-core instruction:
+  // the GEMMs are bound by the per-SM load bandwidth, not by the tensor pipe)
+  static const bool no_dual = getenv("VJF_WIDE_NO_DUAL") != nullptr;
+  // (pays once a GEMM is more than one wave of CTAs; below that the doubled split-K partial sums cost more than they save)
+  const int dual_f = (!no_dual && B > 16384) ? 1 : 0, dual_d = (!no_dual && B > 16384 && D > wg::BN) ? 2 : 0;
+  const int mt = (B + wg::BM * (dual_f ? 2 : 1) - 1) / (wg::BM * (dual_f ? 2 : 1)), nkf = (D + 31) / 32;
   w.ZF = std::max(1, std::min(std::min(4, nkf), h->num_sms / std::max(1, mt)));
-  const int ntd = (D + wg::BN - 1) / wg::BN, nkd = (B + 31) / 32;
-  w.ZD = std::max(1, std::min(std::min(16, nkd), h->num_sms / std::max(1, ntd)));
+  const int ntd = (D + wg::BN * (dual_d ? 2 : 1) - 1) / (wg::BN * (dual_d ? 2 : 1)), nkd = (B + 31) / 32;
+  w.ZD = std::max(1, std::min(std::min(20, nkd), h->num_sms / std::max(1, ntd)));
   int st_f, st_d;
-  const size_t smem_f = wide_gemm_smem(3 + (exact ? 0 : 1), &st_f), smem_d = wide_gemm_smem(3 + (exact ? 0 : 1), &st_d);
+  const size_t smem_f = wide_gemm_smem(3 + (exact ? 0 : 1) + (dual_f ? (exact ? 1 : 2) : 0), &st_f);
+  const size_t smem_d = wide_gemm_smem(3 + (exact ? 0 : 1) + (dual_d ? (exact ? 1 : 2) : 0), &st_d);
   CUtensorMap mW, mWlo, mG, mGlo;
   if (wmap2d(&mW, w.W1T, H, D, w.Dp, wg::BN, false) || wmap2d(&mWlo, w.W1Tlo, H, D, w.Dp, wg::BN, false) ||
       wmap2d(&mG, w.GT, H, B, w.Bp, wg::BM, false) || wmap2d(&mGlo, w.GTlo, H, B, w.Bp, wg::BM, false)) return -2;
@@ -879,6 +944,7 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
   const int nb_grid = std::max(1, std::min(h->num_sms, (pl.lay.n_train + VJF_NT - 1) / VJF_NT));
   static const bool no_overlap = getenv("VJF_WIDE_NO_OVERLAP") != nullptr;
   const bool overlap = !no_overlap && !tm.on;
+  static const bool inkernel_wait = getenv("VJF_WIDE_EVENT_WAIT") == nullptr;
   for (int t = 0; t < T; ++t) {
     StepParams p = pl;
     const float* yt = reinterpret_cast<const float*>(pl.y) + (size_t)t * B * D;
@@ -902,16 +968,19 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     }
     tm.mark("gemm_fwd");
     {
-      wg::Args g = {B, H, D, 0, exact ? 0 : 1, 1, st_f, w.pre, H};
+      wg::Args g = {B, H, D, 0, exact ? 0 : 1, 1, dual_f, st_f, w.pre, H};
       wide_gemm_kernel<<<dim3(mt, 1, w.ZF), wg::NT, smem_f, s>>>(mYk, mYlok, mW, mWlo, g);
     }
     tm.mark("mid");
-    if (t > 0 && overlap) VJF_CUDA_OK(cudaStreamWaitEvent(s, w.ev_rls, 0));  // w_mean / w_chol / noise variances of step t-1
-    if (pl.lik == VJF_LIK_GAUSSIAN) wide_mid_kernel<VJF_LIK_GAUSSIAN><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm);
-    else wide_mid_kernel<VJF_LIK_POISSON><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm);
+    // (the RLS of step t-1 runs on the side stream: the mid kernel waits for its completion counter in-kernel; with the
+    // event-based variant the wait sits in front of the whole kernel)
+    if (t > 0 && overlap && !inkernel_wait) VJF_CUDA_OK(cudaStreamWaitEvent(s, w.ev_rls, 0));
+    const unsigned wait_seq = (overlap && inkernel_wait) ? w.seq : 0u;
+    if (pl.lik == VJF_LIK_GAUSSIAN) wide_mid_kernel<VJF_LIK_GAUSSIAN><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm, wait_seq);
+    else wide_mid_kernel<VJF_LIK_POISSON><<<w.nslots, VJF_NT, (size_t)sm.total * 4, s>>>(p, w, sm, wait_seq);
     tm.mark("gemm_dw");
     {
-      wg::Args g = {H, D, B, 1, 1, exact ? 0 : 1, st_d, w.dWT, w.Dp};
+      wg::Args g = {H, D, B, 1, 1, exact ? 0 : 1, dual_d, st_d, w.dWT, w.Dp};
       wide_gemm_kernel<<<dim3(1, ntd, w.ZD), wg::NT, smem_d, s>>>(mG, mGlo, mYm, mYlom, g);
     }
     tm.mark("reduce");
@@ -928,9 +997,12 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     tm.mark("phase_b");
     if (overlap) {
       vjf_sgd_kernel<<<nb_grid, VJF_NT, 0, s>>>(p);
+      if (w.stamps) wide_stamp_kernel<<<1, 1, 0, s>>>(w.stamps + (p.step0 & 7) * 8 + 6);
       VJF_CUDA_OK(cudaEventRecord(w.ev_sgd, s));
       VJF_CUDA_OK(cudaStreamWaitEvent(w.side, w.ev_sgd, 0));
+      if (w.stamps) wide_stamp_kernel<<<1, 1, 0, w.side>>>(w.stamps + (p.step0 & 7) * 8 + 0);
       vjf_rls_kernel<<<1, VJF_NT, (size_t)p.s_total * sizeof(float), w.side>>>(p);
+      wide_flag_kernel<<<1, 1, 0, w.side>>>(w.flag, ++w.seq, w.stamps ? w.stamps + (p.step0 & 7) * 8 + 1 : nullptr);
       VJF_CUDA_OK(cudaEventRecord(w.ev_rls, w.side));
       if (t == T - 1) VJF_CUDA_OK(cudaStreamWaitEvent(s, w.ev_rls, 0));
       ++g_vjf_launches;
@@ -944,3 +1016,6 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
   VJF_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// development aid: device pointer of the stamp words (NULL unless VJF_WIDE_STAMPS was set at create)
+extern "C" unsigned long long* vjf_wide_stamps(vjf_handle* h) { return (h && h->wide) ? h->wide->stamps : nullptr; }
