@@ -34,7 +34,7 @@ C2 = dict(name="C2-lorenz-poisson", ydim=200, xdim=3, udim=0, n_rbf=50, hidden=[
           trials_per_gpu=4096, T=256)
 # BASELINE.json configs[3]: neural-population scale, 65536 trials sharded over the GPUs (strong scaling), SURVEY.md 8d row C4
 C4 = dict(name="C4-population-poisson", ydim=2000, xdim=8, udim=0, n_rbf=64, hidden=[128], likelihood="poisson",
-          global_trials=65536, T=8)
+          global_trials=65536, T=16)
 # BASELINE.json configs[2]: the tensor-pipe configuration: 1024 RBFs, 16 384 trials, Gaussian observations
 C3 = dict(name="C3-rbf1024-gaussian", ydim=500, xdim=10, udim=0, n_rbf=1024, hidden=[128], likelihood="gaussian",
           trials_per_gpu=16384, T=16)
@@ -466,6 +466,8 @@ def sharded_parity_check(dev, world, rank, seed=5, cfg=None, Bl=192, T=4):
         out.update({"max_err_mu": float(np.abs(got - omu).max()), "max_rel_err_losses": float(np.abs(losses.cpu().numpy() - ol).max() / max(1.0, np.abs(ol).max())),
                     "max_rel_err_parameters": perr, "against": "fp64 oracle of the whole batch (oracle/vjf_oracle.py)"})
     del runner, m
+    import gc
+    gc.collect()  # the handle (and its peer mappings) goes away before the next model connects
     return out
 
 
@@ -654,7 +656,7 @@ def run_ours(args, cfg):
                                                  "frac": fl4 * tps / 1e12 / tf32_peak}}
         del m4, y4
         # (b2) the whole C4 batch on ONE GPU: 65536 trials per step
-        B4f, T4f = c4["global_trials"], 4
+        B4f, T4f = c4["global_trials"], 8
         m4 = VJF.make_model(c4["ydim"], c4["xdim"], 0, c4["n_rbf"], c4["hidden"], c4["likelihood"], max_trials=B4f, seed=99, device=dev)
         m4.load_full_state(bench_state(c4))
         y4 = synthetic_counts_gpu(T4f, B4f, c4["ydim"], c4["xdim"], dev, 31)

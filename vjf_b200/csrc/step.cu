@@ -4,9 +4,41 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
+
+// Process-wide registry of opened CUDA IPC mappings.  cudaIpcOpenMemHandle refuses to map an allocation twice ("resource
+// already mapped"): two handles of one process may see the same peer allocation -- a second model connected while the first
+// is still alive, or a peer that freed its exchange buffer and got the same memory back for the next model.  Mappings are
+// shared and reference-counted instead.
+namespace {
+struct IpcEntry { cudaIpcMemHandle_t h; void* ptr; int refs; int device; };
+std::vector<IpcEntry> g_ipc;
+std::mutex g_ipc_mu;
+int ipc_open(const cudaIpcMemHandle_t& hd, void** out) {
+  int device = 0;
+  VJF_CUDA_OK(cudaGetDevice(&device));
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (auto& e : g_ipc)
+    if (e.device == device && memcmp(&e.h, &hd, sizeof(hd)) == 0) { ++e.refs; *out = e.ptr; return 0; }
+  void* ptr = nullptr;
+  VJF_CUDA_OK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  g_ipc.push_back({hd, ptr, 1, device});
+  *out = ptr;
+  return 0;
+}
+void ipc_close(void* ptr) {
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (size_t i = 0; i < g_ipc.size(); ++i)
+    if (g_ipc[i].ptr == ptr) {
+      if (--g_ipc[i].refs == 0) { cudaIpcCloseMemHandle(ptr); g_ipc.erase(g_ipc.begin() + i); }
+      return;
+    }
+}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // error handling / accounting
@@ -273,7 +305,7 @@ extern "C" int vjf_create(const vjf_config* cfg, float* state, vjf_handle** out)
 extern "C" int vjf_destroy(vjf_handle* h) {
   if (!h) return 0;
   cudaFree(h->partials); cudaFree(h->reduced); cudaFree(h->sync_words); cudaFree(h->w1k); cudaFree(h->uk);
-  for (int r = 0; r < h->comm_world; ++r) if (r != h->comm_rank && h->peer[r]) cudaIpcCloseMemHandle(h->peer[r]);
+  for (int r = 0; r < h->comm_world; ++r) if (r != h->comm_rank && h->peer[r]) ipc_close(h->peer[r]);
   cudaFree(h->xbuf);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->stage_y[i]); cudaFree(h->stage_u[i]); cudaFree(h->stage_eps[i]);
@@ -403,10 +435,12 @@ extern "C" int vjf_comm_connect(vjf_handle* h, int32_t rank, int32_t world, cons
   if (!h || !handles || world < 1 || world > VJF_MAX_RANKS || rank < 0 || rank >= world) { vjf_set_error("bad comm arguments (world <= %d)", VJF_MAX_RANKS); return -1; }
   if (!h->xbuf) { vjf_set_error("call vjf_comm_local_handle first"); return -1; }
   const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < h->comm_world; ++r) if (r != h->comm_rank && h->peer[r]) { ipc_close(h->peer[r]); h->peer[r] = nullptr; }
+  h->comm_world = 0;
   for (int r = 0; r < world; ++r) {
     if (r == rank) { h->peer[r] = h->xbuf; continue; }
     void* ptr = nullptr;
-    VJF_CUDA_OK(cudaIpcOpenMemHandle(&ptr, hs[r], cudaIpcMemLazyEnablePeerAccess));
+    if (ipc_open(hs[r], &ptr)) return -2;
     h->peer[r] = reinterpret_cast<float*>(ptr);
   }
   h->comm_rank = rank; h->comm_world = world; h->comm_epoch = 0;

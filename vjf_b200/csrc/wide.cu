@@ -791,11 +791,14 @@ __global__ void __launch_bounds__(256) wide_exchange_kernel(const StepParams p, 
   if (dead) return;
   const int n4 = (p.PS + 3) >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.world; ++r) {
-      const float4 v = ld_volatile_f4(p.peer[r] + (size_t)(r * 2 + par) * p.PSx + 4 * (size_t)i);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
+    // every peer load of the element is issued before the first add: one NVLink round trip per element, not one per rank
+    float4 v[VJF_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < VJF_MAX_RANKS; ++r)
+      v[r] = (r < p.world) ? ld_volatile_f4(p.peer[r] + (size_t)(r * 2 + par) * p.PSx + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = v[0];
+#pragma unroll
+    for (int r = 1; r < VJF_MAX_RANKS; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
     *reinterpret_cast<float4*>(p.reduced + 4 * (size_t)i) = a;
   }
 }
@@ -991,7 +994,7 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     wide_reduce_rest_kernel<<<(pl.PS - D * H + 31) / 32, 256, 0, s>>>(p, w, red_out);
     if (pl.world > 1) {
       tm.mark("exchange");
-      wide_exchange_kernel<<<std::min(h->num_sms, (pl.PS / 4 + 255) / 256), 256, 0, s>>>(p, epoch);
+      wide_exchange_kernel<<<std::min(4 * h->num_sms, (pl.PS / 4 + 255) / 256), 256, 0, s>>>(p, epoch);
       ++g_vjf_launches;
     }
     tm.mark("phase_b");
