@@ -187,6 +187,11 @@ float* vjf_bigr_buffer(vjf_handle* h, int32_t which);
  * vjf_last_launch_kind() reports 3.  Sharded: the reduced vector is summed by a pull all-reduce over the peer-mapped exchange
  * buffers of vjf_comm_connect.  A non-finite ELBO term skips the SGD step (the split path's rule, vjf/model.py:212-214). */
 
+/* development aid of the wide-observation path: device pointer of its globaltimer stamps (8 steps x 8 words: RLS start / end,
+ * mid kernel start / wait entered / wait left / end of CTA 0, SGD end, end of the last mid CTA), NULL unless VJF_WIDE_STAMPS was set
+ * in the environment when the handle was created (scripts/c4_time.py prints the timeline) */
+unsigned long long* vjf_wide_stamps(vjf_handle* h);
+
 /* status word: OR of VJF_ST_* since the last clear (synchronises the stream) */
 int vjf_get_status(vjf_handle* h, void* stream, uint32_t* out, int32_t clear);
 

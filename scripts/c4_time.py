@@ -22,12 +22,11 @@ for mode in [int(v) for v in os.environ.get("MODES", "0,1").split(",")]:
           f"status {m.status()}, kind {m._lib.vjf_last_launch_kind()}", flush=True)
 if os.environ.get("VJF_WIDE_STAMPS"):
     import ctypes as C, numpy as np
-    f = m._lib.vjf_wide_stamps; f.restype = C.c_void_p; f.argtypes = [C.c_void_p]
-    ptr = f(m._h)
+    ptr = m._lib.vjf_wide_stamps(m._h)
     buf = torch.as_tensor(_lib.DevBuf(ptr, 128), device="cuda").cpu().numpy().view(np.uint64).astype(np.int64).reshape(8, 8)
     t_last = (m._step_index - 1) & 7
     base = buf[(t_last - 3) & 7][2]
     for k in (3, 2, 1, 0):
         r = buf[(t_last - k) & 7]
-        print(f"step -{k}: mid start {(r[2]-base)/1e3:7.1f}  wait {(r[3]-base)/1e3:7.1f} .. {(r[4]-base)/1e3:7.1f}  mid end(CTA0) {(r[5]-base)/1e3:7.1f}  sgd end {(r[6]-base)/1e3:7.1f}"
+        print(f"step -{k}: mid start {(r[2]-base)/1e3:7.1f}  wait {(r[3]-base)/1e3:7.1f} .. {(r[4]-base)/1e3:7.1f}  mid end(CTA0) {(r[5]-base)/1e3:7.1f} (last CTA {(r[7]-base)/1e3:7.1f})  sgd end {(r[6]-base)/1e3:7.1f}"
               f"  rls {(r[0]-base)/1e3:7.1f} .. {(r[1]-base)/1e3:7.1f}")

@@ -129,3 +129,26 @@ def test_c4_shape_takes_the_wide_path(cuda_mod):
     assert np.array_equal(mu, mu2) and np.array_equal(losses, losses2)
     for k in s1:
         assert np.array_equal(s1[k], s2[k]), k
+
+
+def test_wide_path_host_entry_equals_device_entry(cuda_mod):
+    """vjf_run_host (pinned host buffers, chunked H2D) on a wide shape == vjf_run on device buffers, bit for bit."""
+    from vjf_b200 import _lib
+    lik, B, D, d, R, H, T = "poisson", 260, 640, 4, 24, [64], 7
+    rng = np.random.default_rng(12)
+    y, _ = _data(rng, lik, T, B, D, d, 0)
+    eps = rng.normal(size=(T, 2, B, d)).astype(np.float32)
+    a = _make(lik, B, D, d, 0, R, H)
+    st0 = {k: v.clone() for k, v in a.full_state().items()}
+    (mu, lv, losses), kind = _run(a, y, None, eps, 0)
+    assert kind == 3
+    b = _make(lik, B, D, d, 0, R, H)
+    b.load_full_state(st0)
+    yh, eh = torch.as_tensor(y).contiguous().pin_memory(), torch.as_tensor(eps).contiguous().pin_memory()
+    mu_h = torch.empty(T, B, d).pin_memory(); lv_h = torch.empty(T, B, d).pin_memory(); ls_h = torch.empty(T, 4).pin_memory()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    flags = _lib.FLAG_SGD | _lib.FLAG_UPDATE | _lib.FLAG_PRIOR_Q0
+    _lib.check(_lib.load().vjf_run_host(b._h, T, B, p(yh), 0, None, p(eh), 0, 0, flags, b.lr, p(mu_h), p(lv_h), p(ls_h), 3))
+    assert _lib.load().vjf_last_launch_kind() == 3
+    assert np.array_equal(mu, mu_h.numpy()) and np.array_equal(lv, lv_h.numpy()) and np.array_equal(losses, ls_h.numpy())
+    assert torch.equal(a._flat, b._flat)

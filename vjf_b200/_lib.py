@@ -51,6 +51,7 @@ SIGNATURES = {
     "vjf_run_sharded_host": (C.c_int, [_P, _I32, _I32, _I32, _U64, _P, _I32, _P, _P, _U64, _U64, _U32, _F, _P, _P, _P, _I32]),
     "vjf_set_rls_precision": (C.c_int, [_P, _I32]),
     "vjf_bigr_buffer": (_P, [_P, _I32]),
+    "vjf_wide_stamps": (_P, [_P]),
     "vjf_get_status": (C.c_int, [_P, _P, C.POINTER(_U32), _I32]),
     "vjf_philox_normal": (C.c_int, [_U64, _U64, _U64, _I32, _I32, _P, _P]),
     "vjf_launch_count": (_I64, []),

@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(VJF_NT, 1) wide_mid_kernel(const StepParams p,
   }
 
   if (w.stamps && blockIdx.x == 0 && tid == 0) w.stamps[(p.step0 & 7) * 8 + 5] = (unsigned long long)gtime_ns();
+  if (w.stamps && tid == 0) atomicMax(w.stamps + (p.step0 & 7) * 8 + 7, (unsigned long long)gtime_ns());  // last CTA to finish
   // ---- flush: decoder gradients (registers) and the scalar sums ----
 #pragma unroll
   for (int c = 0; c < WM_NC; ++c) {
@@ -723,48 +724,48 @@ __global__ void wide_flag_kernel(unsigned* flag, unsigned value, unsigned long l
 }
 __global__ void wide_stamp_kernel(unsigned long long* stamp) { *stamp = (unsigned long long)gtime_ns(); }
 
-// reduced[y-rows of dW1][j][n] = sum_z dWT[z][n][j]  (transposing, fixed order)
-__global__ void wide_reduce_w1_kernel(const StepParams p, const Wide w, float* __restrict__ out) {
+// The reduced vector in the standard layout, one launch of 1024-thread blocks, every sum in a fixed order:
+//   blocks [0, nW1): reduced[y-rows of dW1][j][n] = sum_z dWT[z][n][j] -- a 32 x 32 tile per block, transposed through shared memory;
+//                    a warp owns a row n of the tile and has all split-K partial sums of its 128-byte segment in flight
+//   the others:      everything else = sums over the mid kernel's slots; a block owns 32 consecutive elements, warp w adds the
+//                    slots w, w + 32, ... (independent row loads), the 32 partial sums meet in warp order
+__global__ void __launch_bounds__(1024) wide_reduce_kernel(const StepParams p, const Wide w, float* __restrict__ out, int ntj, int nW1) {
   __shared__ float t[32][33];
-  const int j0 = blockIdx.x * 32, n0 = blockIdx.y * 32, H = p.H[0], D = p.D;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int n = n0 + r, j = j0 + threadIdx.x;
-    float a = 0.f;
-    if (n < H && j < D)
-      for (int z = 0; z < w.ZD; ++z) a += w.dWT[((size_t)z * H + n) * w.Dp + j];
-    t[r][threadIdx.x] = a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, H = p.H[0], D = p.D;
+  if ((int)blockIdx.x < nW1) {
+    const int j0 = ((int)blockIdx.x % ntj) * 32, n0 = ((int)blockIdx.x / ntj) * 32;
+    const int n = n0 + warp, j = j0 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (n < H && j < D) {
+      const float* src = w.dWT + (size_t)n * w.Dp + j;
+      const size_t zs = (size_t)H * w.Dp;
+      int z = 0;
+      for (; z + 3 < w.ZD; z += 4) { a0 += src[z * zs]; a1 += src[(z + 1) * zs]; a2 += src[(z + 2) * zs]; a3 += src[(z + 3) * zs]; }
+      for (; z < w.ZD; ++z) a0 += src[z * zs];
+    }
+    t[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    const int jo = j0 + warp, no = n0 + lane;
+    if (jo < D && no < H) out[p.lay.mlp_w[0] + (size_t)jo * H + no] = t[lane][warp];
+    return;
   }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int j = j0 + r, n = n0 + threadIdx.x;
-    if (j < D && n < H) out[p.lay.mlp_w[0] + (size_t)j * H + n] = t[threadIdx.x][r];
-  }
-}
-
-// everything else of the reduced vector: sums over the mid kernel's slots.  A block owns 32 consecutive elements; warp w adds
-// the slots w, w + 8, ... (independent 128-byte row loads in flight together), the eight partial sums meet in a fixed order
-__global__ void __launch_bounds__(256) wide_reduce_rest_kernel(const StepParams p, const Wide w, float* __restrict__ out) {
-  __shared__ float part[8][32];
-  const int w0 = p.lay.mlp_w[0], w1 = w0 + p.D * p.H[0];  // the y-rows of dW1 come from the GEMM
+  const int w0 = p.lay.mlp_w[0], w1 = w0 + D * H;  // (the y-rows of dW1 come from the GEMM)
   const int n_rest = p.PS - (w1 - w0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + lane;
+  const int i = ((int)blockIdx.x - nW1) * 32 + lane;
   const int ic = min(i, n_rest - 1);
   const int e = (ic < w0) ? ic : ic + (w1 - w0);
   const float* src = p.partials + e;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float a0 = 0.f, a1 = 0.f;
   int c = warp;
-  for (; c + 24 < w.nslots; c += 32) {
-    a0 += src[(size_t)c * p.PS]; a1 += src[(size_t)(c + 8) * p.PS]; a2 += src[(size_t)(c + 16) * p.PS]; a3 += src[(size_t)(c + 24) * p.PS];
-  }
-  for (; c < w.nslots; c += 8) a0 += src[(size_t)c * p.PS];
-  part[warp][lane] = (a0 + a1) + (a2 + a3);
+  for (; c + 32 < w.nslots; c += 64) { a0 += src[(size_t)c * p.PS]; a1 += src[(size_t)(c + 32) * p.PS]; }
+  if (c < w.nslots) a0 += src[(size_t)c * p.PS];
+  t[warp][lane] = a0 + a1;
   __syncthreads();
   if (warp == 0 && i < n_rest) {
-    float t = part[0][lane];
+    float v = t[0][lane];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) t += part[k][lane];
-    out[e] = t;
+    for (int k = 1; k < 32; ++k) v += t[k][lane];
+    out[e] = v;
   }
 }
 
@@ -990,8 +991,10 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     // sharded: the local sums go into this rank's exchange buffer (parity slot of the epoch), the peers pull them
     const unsigned epoch = pl.epoch0 + (unsigned)t + 1;
     float* red_out = (pl.world > 1) ? pl.peer[pl.rank] + ((size_t)pl.rank * 2 + (epoch & 1)) * PSx : p.reduced;
-    wide_reduce_w1_kernel<<<dim3((D + 31) / 32, (H + 31) / 32), dim3(32, 8), 0, s>>>(p, w, red_out);
-    wide_reduce_rest_kernel<<<(pl.PS - D * H + 31) / 32, 256, 0, s>>>(p, w, red_out);
+    {
+      const int ntj = (D + 31) / 32, nW1 = ntj * ((H + 31) / 32);
+      wide_reduce_kernel<<<nW1 + (pl.PS - D * H + 31) / 32, 1024, 0, s>>>(p, w, red_out, ntj, nW1);
+    }
     if (pl.world > 1) {
       tm.mark("exchange");
       wide_exchange_kernel<<<std::min(4 * h->num_sms, (pl.PS / 4 + 255) / 256), 256, 0, s>>>(p, epoch);
@@ -1012,7 +1015,7 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
     } else {
       vjf_phase_b_kernel<<<nb_grid, VJF_NT, (size_t)p.s_total * sizeof(float), s>>>(p);
     }
-    g_vjf_launches += 7;
+    g_vjf_launches += 6;
     tm.mark("end");
   }
   tm.report();
