@@ -421,7 +421,7 @@ def tensor_flops_per_trial_step(cfg):
 def sharded_parity_check(dev, world, rank, seed=5, cfg=None, Bl=192, T=4):
     """Short sharded run (C2 shapes by default, 192 trials per rank, 4 steps, noise tape) against the fp64 oracle of the WHOLE
     batch on rank 0, and bitwise identity of the replicas: SCALE lines carry the evidence that the multi-GPU path computes the
-    same thing (the driver's GPU tests run on one GPU only).  With cfg = C4 the wide-observation path and its pull all-reduce."""
+    same thing (the driver's GPU tests run on one GPU only).  With cfg = C4 the wide-observation path and its push all-reduce."""
     import torch
     import torch.distributed as dist
     from vjf_b200.model import VJF
@@ -747,7 +747,7 @@ def run_ours(args, cfg):
         tps = c4["global_trials"] * T4 / (ms * 1e-3)
         ach = ALGO_BYTES_PER_TRIAL_STEP(c4) * tps / world / 1e9
         extras["c4_strong_scaling"] = {"workload": f"{c4['name']}: ydim 2000 xdim 8 n_rbf 64 hidden [128], {c4['global_trials']} trials over {world} GPUs "
-                                                   f"({B4} per GPU) x {T4} steps, " + ("wide-observation launch sequence, pull all-reduce over NVLink peer memory" if int(lib.vjf_last_launch_kind()) == 3 else "in-kernel NVLink all-reduce"), "scaling": "strong",
+                                                   f"({B4} per GPU) x {T4} steps, " + ("wide-observation launch sequence, push all-reduce over NVLink peer memory" if int(lib.vjf_last_launch_kind()) == 3 else "in-kernel NVLink all-reduce"), "scaling": "strong",
                                        "value": tps, "unit": "trial-steps/s", "us_per_time_step": ms / T4 * 1e3,
                                        "kernel_kind": int(lib.vjf_last_launch_kind()), "status_word": int(m4.status()),
                                        "roofline_per_gpu": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}}

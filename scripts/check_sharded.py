@@ -14,7 +14,7 @@ from vjf_b200.model import VJF
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-# CS_D > 480 exercises the wide-observation path (csrc/wide.cu) and its pull all-reduce over peer memory
+# CS_D > 480 exercises the wide-observation path (csrc/wide.cu) and its push all-reduce over peer memory
 D, d, R, H, Bg, T = int(os.environ.get("CS_D", 60)), int(os.environ.get("CS_XD", 3)), int(os.environ.get("CS_R", 20)), [int(os.environ.get("CS_H", 16))], int(os.environ.get("CS_B", 200)), int(os.environ.get("CS_T", 12))
 for lik in ("poisson", "gaussian"):
     torch.manual_seed(7)  # identical data on every rank

@@ -10,7 +10,7 @@
 //                  likelihood + ELBO + hand-derived backward (vjf/model.py:97-154, :209), RLS statistics (vjf/module.py:94-96);
 //                  hands g_pre^T (raw + lo) to the second GEMM
 //   GEMM dW        dW1[:D]^T[n][j] = sum_trials g_pre[trial][n] y_t[trial][j]        (backward of recognition.py:38)
-//   reduce         slot sums + split-K partial sums -> the reduced vector in the standard layout; (sharded: pull all-reduce over
+//   reduce         slot sums + split-K partial sums -> the reduced vector in the standard layout; (sharded: push all-reduce over
 //                  NVLink peer memory) ; vjf_phase_b_kernel: clip + SGD, losses, running variances, RLS (k_split.cu)
 //
 // GEMM kernel: a pure TMA -> tcgen05 pipeline (no in-kernel operand pass): 128 x 128 output tile, fp32 accumulators in tensor
@@ -729,7 +729,9 @@ __global__ void wide_stamp_kernel(unsigned long long* stamp) { *stamp = (unsigne
 //                    a warp owns a row n of the tile and has all split-K partial sums of its 128-byte segment in flight
 //   the others:      everything else = sums over the mid kernel's slots; a block owns 32 consecutive elements, warp w adds the
 //                    slots w, w + 32, ... (independent row loads), the 32 partial sums meet in warp order
-__global__ void __launch_bounds__(1024) wide_reduce_kernel(const StepParams p, const Wide w, float* __restrict__ out, int ntj, int nW1) {
+// Sharded run (push > 0): the sums are stored straight into the inbox slot (this rank, parity) of EVERY rank's peer-mapped exchange
+// buffer -- posted NVLink writes that leave while the other ranks are still computing; `out` is then unused.
+__global__ void __launch_bounds__(1024) wide_reduce_kernel(const StepParams p, const Wide w, float* __restrict__ out, int ntj, int nW1, int push, int par) {
   __shared__ float t[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, H = p.H[0], D = p.D;
   if ((int)blockIdx.x < nW1) {
@@ -746,7 +748,12 @@ __global__ void __launch_bounds__(1024) wide_reduce_kernel(const StepParams p, c
     t[warp][lane] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     const int jo = j0 + warp, no = n0 + lane;
-    if (jo < D && no < H) out[p.lay.mlp_w[0] + (size_t)jo * H + no] = t[lane][warp];
+    if (jo < D && no < H) {
+      const size_t e = p.lay.mlp_w[0] + (size_t)jo * H + no;
+      const float v = t[lane][warp];
+      if (push) { for (int r = 0; r < p.world; ++r) p.peer[r][(size_t)(p.rank * 2 + par) * p.PSx + e] = v; }
+      else out[e] = v;
+    }
     return;
   }
   const int w0 = p.lay.mlp_w[0], w1 = w0 + D * H;  // (the y-rows of dW1 come from the GEMM)
@@ -765,13 +772,15 @@ __global__ void __launch_bounds__(1024) wide_reduce_kernel(const StepParams p, c
     float v = t[0][lane];
 #pragma unroll
     for (int k = 1; k < 32; ++k) v += t[k][lane];
-    out[e] = v;
+    if (push) { for (int r = 0; r < p.world; ++r) p.peer[r][(size_t)(p.rank * 2 + par) * p.PSx + e] = v; }
+    else out[e] = v;
   }
 }
 
-// Sharded run: pull all-reduce of the reduced vector over NVLink peer memory.  Every rank's local sums sit in its own
-// exchange buffer (parity slot of the epoch); block 0 raises this rank's flag on every peer, every block waits until all
-// ranks have raised theirs here, then the vector is summed in rank order straight from the peers' buffers.
+// Sharded run: all-reduce of the reduced vector over NVLink peer memory, push model.  The reduce launch of every rank has
+// stored its sums into slot (rank, parity) of every rank's exchange buffer (the kernel boundary completes those writes at
+// system scope); block 0 raises this rank's flag on every peer, every block waits until all ranks have raised theirs here,
+// then the vector is the sum of the local inbox slots in rank order -- identical on every rank.
 __global__ void __launch_bounds__(256) wide_exchange_kernel(const StepParams p, unsigned epoch) {
   const int par = epoch & 1, nchx = p.PSx >> 7;
   const size_t flag_off = (size_t)p.world * 2 * p.PSx;
@@ -791,12 +800,12 @@ __global__ void __launch_bounds__(256) wide_exchange_kernel(const StepParams p, 
   __syncthreads();
   if (dead) return;
   const int n4 = (p.PS + 3) >> 2;
+  const float* inbox = p.peer[p.rank];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-    // every peer load of the element is issued before the first add: one NVLink round trip per element, not one per rank
     float4 v[VJF_MAX_RANKS];
 #pragma unroll
     for (int r = 0; r < VJF_MAX_RANKS; ++r)
-      v[r] = (r < p.world) ? ld_volatile_f4(p.peer[r] + (size_t)(r * 2 + par) * p.PSx + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[r] = (r < p.world) ? ld_volatile_f4(inbox + (size_t)(r * 2 + par) * p.PSx + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a = v[0];
 #pragma unroll
     for (int r = 1; r < VJF_MAX_RANKS; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
@@ -988,12 +997,12 @@ int vjf_wide_time_loop(vjf_handle* h, StepParams& p0, int T, int B, cudaStream_t
       wide_gemm_kernel<<<dim3(1, ntd, w.ZD), wg::NT, smem_d, s>>>(mG, mGlo, mYm, mYlom, g);
     }
     tm.mark("reduce");
-    // sharded: the local sums go into this rank's exchange buffer (parity slot of the epoch), the peers pull them
+    // sharded: the sums are pushed into every rank's exchange buffer (inbox slot of this rank, parity of the epoch)
     const unsigned epoch = pl.epoch0 + (unsigned)t + 1;
-    float* red_out = (pl.world > 1) ? pl.peer[pl.rank] + ((size_t)pl.rank * 2 + (epoch & 1)) * PSx : p.reduced;
+    float* red_out = p.reduced;
     {
       const int ntj = (D + 31) / 32, nW1 = ntj * ((H + 31) / 32);
-      wide_reduce_kernel<<<nW1 + (pl.PS - D * H + 31) / 32, 1024, 0, s>>>(p, w, red_out, ntj, nW1);
+      wide_reduce_kernel<<<nW1 + (pl.PS - D * H + 31) / 32, 1024, 0, s>>>(p, w, red_out, ntj, nW1, pl.world > 1 ? 1 : 0, (int)(epoch & 1));
     }
     if (pl.world > 1) {
       tm.mark("exchange");
