@@ -831,6 +831,12 @@ static EncodeTiledFn wide_encode_fn() {
   return fn;
 }
 
+// L2 promotion of the TMA requests (a box row is one 128-byte request; its neighbour in the row is the next K chunk's)
+static CUtensorMapL2promotion wide_l2_promotion() {
+  static const int v = getenv("VJF_WIDE_L2PROMO") ? atoi(getenv("VJF_WIDE_L2PROMO")) : 128;
+  return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+}
+
 // [rows][cols] fp32 row-major, row stride ld floats: boxes of {32 columns, box_rows rows}
 static int wmap2d(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows, bool atom32) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -838,7 +844,7 @@ static int wmap2d(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, 
   const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = wide_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, wide_l2_promotion(),
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { vjf_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -2; }
   return 0;
