@@ -95,6 +95,7 @@ class ShardedVJF:
                 _lib.check(lib.vjf_run_sharded(m._h, T, B, Bg, off, p(y), ydt, p(u), None, None, p(eps), m.seed, m._step_index, f,
                                                m.lr, p(mu), p(lv), p(losses), s))
             m._step_index += T
+            self._check_exchange()
             return mu, lv, losses
         for t in range(T):
             f = plan_step(t, sgd, update, warm_up, frozen)
@@ -107,6 +108,14 @@ class ShardedVJF:
             _lib.check(lib.vjf_step_phase_b(m._h, Bg, f, m.lr, p(losses[t]), s))
         m._step_index += T
         return mu, lv, losses
+
+    def _check_exchange(self):
+        """A lost peer turns into VJF_ST_COMM_TIMEOUT (the kernel stops applying updates): raise instead of returning a
+        trajectory whose replicas have silently diverged.  Reads the status word without clearing the other bits."""
+        st = C.c_uint32(0)
+        _lib.check(self.m._lib.vjf_get_status(self.m._h, self.m._stream(), C.byref(st), 0))
+        if st.value & _lib.ST_COMM_TIMEOUT:
+            raise RuntimeError("vjf_b200: a peer's contribution did not arrive within the time-out (VJF_ST_COMM_TIMEOUT)")
 
     def _global_batch(self, B):
         """(total trials over all ranks, first global trial index of this rank): an exclusive prefix sum over the ranks'

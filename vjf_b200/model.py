@@ -265,6 +265,10 @@ class VJF(nn.Module):
         out = C.c_uint32(0)
         _lib.check(self._lib.vjf_get_status(self._h, self._stream(), C.byref(out), 1 if clear else 0))
         st = out.value
+        if st & _lib.ST_COMM_TIMEOUT:
+            # a peer's contribution to the in-kernel all-reduce (sharded run) or the side-stream RLS launch of the wide-observation
+            # path did not arrive within the time-out: nothing was applied after that point, the replicas / the state are not valid
+            raise RuntimeError("vjf_b200: exchange time-out (VJF_ST_COMM_TIMEOUT): the run is invalid")
         if st & _lib.ST_CHOL_FAILED:
             warnings.warn("RLS failed.")  # vjf/module.py:112
         if st & _lib.ST_MSE_NONFINITE:
