@@ -368,21 +368,32 @@ static __device__ __forceinline__ void tk_lk_rows(const StepParams& p, TkAcc<DX>
 #pragma unroll
       for (int k = 0; k < DX; ++k) { acc.gdw[k] = fmaf(g, xt[k], acc.gdw[k]); gx[q][k] = g * w[k]; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    // transposed warp reduction of the TK_LK_RB x DX partial sums: at every step a lane keeps one half of its values and hands
+    // the other half to its partner, so N values over 32 lanes cost N - 1 + (5 - log2 N) shuffles instead of 5 N; lane L ends
+    // with the full sum of value L >> (5 - log2 N) and stores it itself
+    {
+      constexpr int DXP = DX <= 2 ? 2 : (DX <= 4 ? 4 : 8), N = TK_LK_RB * DXP, LOGN = DXP == 2 ? 3 : (DXP == 4 ? 4 : 5);
+      float v[N];
 #pragma unroll
       for (int q = 0; q < TK_LK_RB; ++q)
 #pragma unroll
-        for (int k = 0; k < DX; ++k) gx[q][k] += __shfl_xor_sync(0xffffffffu, gx[q][k], o);
-    if (lane == 0) {
+        for (int k = 0; k < DXP; ++k) v[q * DXP + k] = (k < DX) ? gx[q][k < DX ? k : 0] : 0.f;
+      int o = 16;
 #pragma unroll
-      for (int q = 0; q < TK_LK_RB; ++q) {
-        const int b = bb + q * pl.RS;
-        if (b < nb) {
+      for (int h = N / 2; h >= 1; h >>= 1, o >>= 1) {
+        const bool up = lane & o;
 #pragma unroll
-          for (int k = 0; k < DX; ++k)
-            if (DX == d || k < d) gxp_s[(cy * TBR + b) * d + k] = gx[q][k];
+        for (int i = 0; i < h; ++i) {
+          const float keep = up ? v[i + h] : v[i], send = up ? v[i] : v[i + h];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
+      }
+#pragma unroll
+      for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+      if ((lane & ((32 >> LOGN) - 1)) == 0) {
+        const int idx = lane >> (5 - LOGN), q = idx / DXP, k = idx - q * DXP;
+        const int b = bb + q * pl.RS;
+        if (b < nb && k < d) gxp_s[(cy * TBR + b) * d + k] = v[0];
       }
     }
   }
