@@ -26,7 +26,7 @@ lib.vjf_debug_set_stamps(None)
 s = dbg.cpu().double()
 print(f"B={B} D={D} R={R} H={H} {lik}: {e0.elapsed_time(e1) / T * 1e3:.1f} us per step, kind {lib.vjf_last_launch_kind()} status {m.status()}")
 lo, hi = 4, T - 2
-names = {0: "tile start", 1: "extras+eps", 2: "xs", 3: "wait DW(prev)", 4: "phi written", 5: "wait y (TMA)", 6: "X cols + lo image (CX)", 7: "wait D1 (FWD MMA)",
+names = {0: "tile start", 1: "extras+eps", 2: "xs", 3: "wait DW(prev)", 4: "wait y (TMA)", 5: "X cols + lo image (CX)", 6: "phi written (CPHI)", 7: "wait D1 (FWD MMA)",
          8: "E1 tanh", 9: "heads/xt", 10: "permute in", 11: "LK decoder+likelihood", 12: "wait FL (QUAD MMA)", 13: "phi permute + dx + FL epilogue",
          14: "wait ctrl3 (RLS tail)", 15: "S7 dyn/entropy", 16: "wait GRAM", 17: "GS g_pre + head grads (CG)"}
 print(" compute warps, first tile (us after run_tiles entry; delta):")
@@ -45,9 +45,18 @@ for i in range(32, 42):
     print(f"  {i:2d} {cn[i]:40s} {v:8.2f}")
 sn = {49: "tiles done (before flush)", 50: "flush done", 51: "barrier 1 released", 52: "B1 done", 53: "trial barrier released"}
 print(" step level (us after run_tiles entry of the SAME step's tiles):")
-for i in (49, 50):
+sn.update({54: "flush: tensor-memory accumulators stored", 55: "flush: register accumulators in scratch"})
+for i in (49, 54, 55, 50):
     print(f"  {sn[i]:40s} {(s[lo:hi, i] - base).mean().item() / 1e3:8.2f}")
 # stamps 51..53 of step t follow the tiles of step t (entered during step t-1)
 for i in (51, 52, 53):
     print(f"  {sn[i]:40s} {(s[lo:hi, i] - base).mean().item() / 1e3:8.2f}")
 print(f"  next run_tiles entry                     {(s[lo + 1:hi + 1, 48] - base).mean().item() / 1e3:8.2f}")
+rn = {30: "RLS: statistics arrived (independent part P, P W done before)", 25: "RLS: P' / g built", 26: "RLS: sweep starts", 27: "RLS: sweep done",
+      28: "RLS: columns scaled, w_pchol / w_chol / images committed", 29: "RLS: W' done, ctrl5 published", 24: "B2: losses read out (deferred: after the factorisation)"}
+print(" RLS CTA (us after barrier 1 of the same step):")
+b1 = s[lo:hi, 51]
+for i in (30, 25, 26, 27, 28, 29, 24):
+    print(f"  {i:2d} {rn[i]:60s} {(s[lo:hi, i] - b1).mean().item() / 1e3:8.2f}")
+print(f"  trial CTAs: B1 done {(s[lo:hi, 52] - b1).mean().item() / 1e3:8.2f}  trial barrier released {(s[lo:hi, 53] - b1).mean().item() / 1e3:8.2f}")
+print(f"  next barrier 1 released {(s[lo + 1:hi + 1, 51] - b1).mean().item() / 1e3:8.2f}")

@@ -41,6 +41,7 @@ struct TilePlan {
   int RS;                    // row splits of the likelihood stage (warps per observation chunk)
   // shared memory: byte offsets from the 1024-byte aligned base
   int o_in[2], o_inlo, o_pg, o_ring, o_uk, o_f, scratch_bytes;
+  int flush_floats, flush_stage;  // floats of the per-step flush scratch; 1: a [128][N + 4] staging block behind it (accumulator flush by whole lines)
   // float area: float offsets from o_f
   int f_hs, ldhs, f_dec, f_hm, f_hv, f_cen, f_iw, f_ex, f_eps, f_xu, f_xt, f_mt, f_lt, f_pm, f_dx, f_gxt, f_gmt, f_glt, f_plv,
       f_gxp, f_red, f_misc, f_bar, f_total;

@@ -68,7 +68,7 @@ static __device__ __forceinline__ void tk_run_tiles(const StepParams& p, const C
   }
   __syncthreads();
   TK_STAMP(p, t, 0, 0, 49);
-  tk_flush_step<DX>(p, sb, tmem, acc, ntl > 0);
+  tk_flush_step<DX>(p, sb, tmem, acc, ntl > 0, t);
   TK_STAMP(p, t, 0, 0, 50);
   it0 += (uint32_t)ntl;
 }

@@ -796,31 +796,57 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
   float4* red = reinterpret_cast<float4*>(sm + p.s_b1);  // [16][32] float4
   const int c_lo = p.red_begin >> 7, nchunks = (p.PS + 127) >> 7;
   const int stat_chunk0 = p.pa >> 7;  // chunks >= this one hold RLS statistics / loss sums
-  for (int ch = nchunks - 1 - cta; ch >= c_lo; ch -= nctas) {
+  // Rounds of nctas chunks from the end of the vector; odd rounds are dealt out in the opposite CTA order, so that the few
+  // chunks beyond a whole number of rounds land on the CTAs that hold gradient chunks, not on those that hold the statistics
+  // chunks the RLS waits for.  A CTA that owns a chunk in two consecutive rounds reduces them side by side, eight warps
+  // each, instead of one after the other: the phase lasts one chunk time for every CTA.
+  const int top = nchunks - 1;
+  for (int k = 0; top - k * nctas >= c_lo; k += 2) {
+    const int chA = top - k * nctas - cta, chB = top - (k + 2) * nctas + 1 + cta;  // round k forwards, round k + 1 backwards
+    const bool vA = chA >= c_lo, vB = chB >= c_lo;
+    if (!vA && !vB) continue;
+    const bool two = vA && vB;
+    const int wpg = two ? VJF_NWARP / 2 : VJF_NWARP;   // warps per chunk
+    const int grp = warp / wpg, wi = warp - grp * wpg;
+    const int ch = two ? (grp ? chB : chA) : (vA ? chA : chB);
     const int e0 = (ch << 7) + (lane << 2);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e0 < p.PS) {
       const float* q = src + e0;
-      // up to 10 slots per warp (nslots <= 160): issue every load before the first add, one L2 round trip in all
-      float4 v[10];
+      if (!two) {
+        // up to 10 slots per warp (nslots <= 160): issue every load before the first add, one L2 round trip in all
+        float4 v[10];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        const int c = warp + j * VJF_NWARP;
-        v[j] = (c < nslots) ? *reinterpret_cast<const float4*>(q + (size_t)c * p.PS) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int j = 0; j < 10; ++j) {
+          const int c = warp + j * VJF_NWARP;
+          v[j] = (c < nslots) ? *reinterpret_cast<const float4*>(q + (size_t)c * p.PS) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-      for (int j = 0; j < 10; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
-      for (int c = warp + 10 * VJF_NWARP; c < nslots; c += VJF_NWARP) {
-        const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
-        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        for (int j = 0; j < 10; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        for (int c = warp + 10 * VJF_NWARP; c < nslots; c += VJF_NWARP) {
+          const float4 v0 = *reinterpret_cast<const float4*>(q + (size_t)c * p.PS);
+          acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        }
+      } else {
+        // eight warps per chunk: two rounds of ten slots each (nslots <= 160)
+#pragma unroll 1
+        for (int base = wi; base < nslots; base += 10 * (VJF_NWARP / 2)) {
+          float4 v[10];
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            const int c = base + j * (VJF_NWARP / 2);
+            v[j] = (c < nslots) ? *reinterpret_cast<const float4*>(q + (size_t)c * p.PS) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 10; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
       }
     }
     red[warp * 32 + lane] = acc;
     __syncthreads();
-    if (warp == 0) {
-      float4 t = red[lane];
-#pragma unroll
-      for (int w = 1; w < VJF_NWARP; ++w) { const float4 v = red[w * 32 + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    if (wi == 0) {
+      float4 t = red[warp * 32 + lane];
+      for (int w = 1; w < wpg; ++w) { const float4 v = red[(warp + w) * 32 + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
       if (epoch) {
         // ---- in-kernel all-reduce over NVLink peer memory: push this rank's chunk into every rank's inbox, raise the
         //      (source rank, chunk) flag there, wait for the same chunk of every rank, add in rank order ----
@@ -884,7 +910,10 @@ static __device__ void phase_b1(const StepParams& p, float* sm, const float* src
       }
     }
     __syncthreads();
-    if (signal && ch >= stat_chunk0 && tid == 0) { __threadfence(); atomicAdd(signal, 1u); }
+    if (signal && tid == 0) {
+      const unsigned n = ((vA && chA >= stat_chunk0) ? 1u : 0u) + ((vB && chB >= stat_chunk0) ? 1u : 0u);
+      if (n) { __threadfence(); atomicAdd(signal, n); }
+    }
   }
 }
 
@@ -975,7 +1004,7 @@ __device__ __forceinline__ bool ldl_sweep_range(float (&v)[RPW][CPL], const int 
 
 template <int CPL, int RPW, int NW>
 static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv, const float* A, const float* bv, int t,
-                                       double* resid_out, const unsigned* wait_ctr = nullptr, unsigned wait_val = 0) {
+                                       double* resid_out, const unsigned* wait_ctr = nullptr, unsigned wait_val = 0, bool* noise_done = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int R = p.R, d = p.d, NR = 2 * R + d;
   // NW warps take part (row r lives in warp r % NW)
@@ -1109,7 +1138,11 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
   fail = misc[0] != 0.f;
   VJF_STAMP(p, t, 27);
   if (fail) return false;
-  // ---- scale the columns and commit: w_pchol = L, w_chol = L^-T, z ; then W' = w_chol z ----
+  // ---- scale the columns ; z and w_chol = L^-T into shared memory ; W' = w_chol z ; publish ; residual ; THEN the rest of the
+  //      commit.  What the trial CTAs of the next step wait for (w_chol / w_mean, in the tile pipeline their operand images)
+  //      is written first -- the images by whole 128-byte rows from shared memory instead of one scattered store per element
+  //      from the register layout -- and everything nobody waits for (w_pchol, w_precision, w_chol of the tile pipeline)
+  //      after the residual. ----
   float* Lout = st + p.lay.w_pchol;
   float* Uout = st + p.lay.w_chol;
   float* Pout = st + p.lay.w_precision;
@@ -1120,26 +1153,25 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     sdv[ci] = (j < R) ? sqrtf(dvec[j]) : 1.f;
     isd[ci] = 1.0f / sdv[ci];
   }
+  const bool images = p.tp.on != 0;
 #pragma unroll
   for (int ri = 0; ri < RPW; ++ri) {
     const int r = active_warp ? warp + NW * ri : (1 << 20);
-    if (r >= NR) continue;
+    if (r >= NR || r < R) continue;
 #pragma unroll
     for (int ci = 0; ci < CPL; ++ci) {
       const int j = lane + 32 * ci;
       if (j >= R) continue;
       const float x = v[ri][ci] * isd[ci];
-      if (r < R) {
-        Lout[r * R + j] = (j < r) ? x : ((j == r) ? sdv[ci] : 0.f);
-        if (ri < PR && j <= r) { Pout[r * R + j] = v0[ri][ci]; Pout[j * R + r] = v0[ri][ci]; }
-      } else if (r < R + d) {
+      if (r < R + d) {
         zbuf[(r - R) * R + j] = x;
       } else {
         const int c = r - R - d;
         const float uv = (j >= c) ? x : 0.f;
-        Uout[c * R + j] = uv;
-        if (p.use_tma) p.u_mirror[c * p.ldu + j] = uv;  // row-padded mirror: the TMA source of the next back half
-        if (p.tp.on) uk_store(p, j, c, uv);
+        if (!images) {
+          Uout[c * R + j] = uv;
+          if (p.use_tma) p.u_mirror[c * p.ldu + j] = uv;  // row-padded mirror: the TMA source of the next back half
+        }
         Qs[c * ldq + j] = uv;
       }
     }
@@ -1158,9 +1190,23 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
     if (j < R) s0 = fmaf(q[j], z[j], s0);
     const float w = s0 + s1;
     Wout[i] = w; Ws[i] = w;
-    if (p.tp.on) uk_store(p, p.tp.Rk + k, c, w);
   }
   __syncthreads();
+  if (images) {
+    // operand images of the tile pipeline ([w_chol^T ; w_mean^T], hi | lo, K-major SW128; see uk_store): a warp writes one
+    // 128-byte image row (32 contraction indices of one output column) per store
+    const int nchunk = (p.tp.Rk + 31) >> 5, NQ = p.tp.NQ, lo_off = p.tp.ukimg >> 2;
+    for (int task = warp; task < (R + d) * nchunk; task += VJF_NWARP) {
+      const int row = task / nchunk, chunk = task - row * nchunk;
+      const int c = chunk * 32 + lane;
+      const float val = (c < R) ? (row < R ? Qs[c * ldq + row] : Ws[c * d + (row - R)]) : 0.f;
+      const int nq = row < R ? row : p.tp.Rk + (row - R);
+      const int off = (chunk * NQ + nq) * 32 + ((((lane >> 2) ^ (nq & 7)) << 2) | (lane & 3));
+      p.uk[off] = val;
+      p.uk[lo_off + off] = val - tf32_trunc_f(val);
+    }
+    __syncthreads();
+  }
   // overlapped schedule: w_chol / w_mean of this step are final -- let the trial CTAs stage them for the back half of the
   // next step while the residual / state-noise update below is still running
   if (p.overlap && !p.init_mode && tid == 0) { __threadfence(); st_release_gpu_u32(p.ctrl + 5, (unsigned)(t + 1)); }
@@ -1184,6 +1230,58 @@ static __device__ bool rls_factor_regs(const StepParams& p, float* sm, float iv,
   }
   for (int i = tid; i < R * d; i += VJF_NT) acc -= 2.0 * (double)Ws[i] * (double)bs[i];
   *resid_out = block_sum_d(acc, dred);
+  // Overlapped schedules: the trial CTAs of the next step wait for the state-noise variance (ctrl[3]) right after the dynamics
+  // read-out -- update it (vjf/model.py:373-377) and publish it HERE, before the part of the commit nobody waits for.  (The
+  // caller finds *noise_done set and only reads out the losses; its own release of ctrl[3] repeats the same value.)
+  if (noise_done) {
+    *noise_done = false;
+    if (p.overlap && !p.init_mode && p.lik == VJF_LIK_POISSON) {
+      if (tid == 0) {
+        const float Bf = (float)p.Bglobal, gam = st[p.lay.tr_logvar];
+        const double tot = *resid_out + (double)p.reduced[p.ps + SC_SDX];
+        const float mse = (float)(fmax(tot, 0.0) / ((double)p.Bglobal * (double)d));
+        float n_new;
+        const float var = running_var_f(expf(gam), st[p.lay.tr_n], mse, Bf, 500.f, &n_new);
+        st[p.lay.tr_logvar] = logf(var);
+        st[p.lay.tr_n] = n_new;
+        __threadfence();
+        st_release_gpu_u32(p.ctrl + 3, (unsigned)(t + 1));
+      }
+      *noise_done = true;
+    }
+  }
+  // ---- the rest of the commit: w_pchol = L and (tile pipeline) w_chol from the registers, row by row; w_precision = P' both
+  //      triangles through shared memory (the w_chol buffer is dead), so that the global rows are written whole ----
+  __syncthreads();
+#pragma unroll
+  for (int ri = 0; ri < RPW; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
+    if (r >= NR || (r >= R && r < R + d)) continue;
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      if (j >= R) continue;
+      const float x = v[ri][ci] * isd[ci];
+      if (r < R) {
+        Lout[r * R + j] = (j < r) ? x : ((j == r) ? sdv[ci] : 0.f);
+      } else if (images) {
+        const int c = r - R - d;
+        Uout[c * R + j] = (j >= c) ? x : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int ri = 0; ri < PR; ++ri) {
+    const int r = active_warp ? warp + NW * ri : (1 << 20);
+    if (r >= R) continue;
+#pragma unroll
+    for (int ci = 0; ci < CPL; ++ci) {
+      const int j = lane + 32 * ci;
+      if (j <= r) { Qs[r * ldq + j] = v0[ri][ci]; Qs[j * ldq + r] = v0[ri][ci]; }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < R * R; i += VJF_NT) { const int r = i / R, j = i - r * R; Pout[i] = Qs[r * ldq + j]; }
   return true;
 }
 
@@ -1431,7 +1529,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
   // mean squared increment (model.py:384-385)
   const float iv = p.init_mode ? (Bf * (float)d) / scal[SC_SDX] : 1.0f / expf(gam);
   __syncthreads();
-  bool have_resid = false;
+  bool have_resid = false, noise_done = false;  // noise_done: the factorisation already updated and published the state-noise variance
   double resid = 0.0;
   if (!warm) {
     bool ok;
@@ -1440,11 +1538,11 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     (void)nr16;
     (void)nr8;
     if (p.rls64) ok = rls_factor_f64(p, sm, iv, A, bv);
-    else if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
-    else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
-    else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
-    else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
-    else if (R <= 128) { ok = rls_factor_regs<4, 17, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val); have_resid = ok; }
+    else if (R <= 64 && nr16 <= 5) { ok = rls_factor_regs<2, 5, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val, &noise_done); have_resid = ok; }
+    else if (R <= 64 && nr16 <= 7) { ok = rls_factor_regs<2, 7, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val, &noise_done); have_resid = ok; }
+    else if (R <= 64) { ok = rls_factor_regs<2, 9, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val, &noise_done); have_resid = ok; }
+    else if (R <= 128 && nr16 <= 13) { ok = rls_factor_regs<4, 13, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val, &noise_done); have_resid = ok; }
+    else if (R <= 128) { ok = rls_factor_regs<4, 17, 16>(p, sm, iv, A, bv, t, &resid, defer ? wait_ctr : nullptr, wait_val, &noise_done); have_resid = ok; }
     else ok = rls_factor_smem(p, sm, iv, A, bv);
     if (!ok && tid == 0) atomicOr(p.status, (unsigned)VJF_ST_CHOL_FAILED);
     __syncthreads();
@@ -1475,7 +1573,7 @@ static __device__ void phase_b2(const StepParams& p, float* sm, int t, unsigned 
     tot = block_sum_d(acc, dred) + (double)scal[SC_SDX];
   }
   {
-    if (tid == 0) {
+    if (tid == 0 && !noise_done) {
       const float mse = (float)(fmax(tot, 0.0) / ((double)p.Bglobal * (double)d));
       if (p.init_mode) { st[p.lay.tr_logvar] = logf(mse); return; }  // model.py:387-388
       float n_new;

@@ -167,7 +167,9 @@ int vjf_tile_plan(vjf_handle* h, StepParams& p, const void* y, int y_dtype, int 
   // scratch of the per-step flush (register accumulators of 15 warps) and workspace of the shared phases B1 / B2
   const int DX = d <= 2 ? 2 : (d == 3 ? 3 : (d == 4 ? 4 : 8));
   const int flush_floats = TK_NCW * (DX + 1) * 32 + TK_NCW * 2 * pl.HC * DX * 32 + 16 * VJF_NSCAL + 16 + 16;
-  if (flush_floats * 4 > pl.scratch_bytes) return 0;
+  pl.flush_floats = (flush_floats + 31) & ~31;
+  if (pl.flush_floats * 4 > pl.scratch_bytes) return 0;
+  pl.flush_stage = ((pl.flush_floats + 128 * (std::max(pl.NQ, H) + 4)) * 4 <= pl.scratch_bytes) ? 1 : 0;  // staging block of the accumulator flush
   size_t b2 = 2 * 16 * 17 + p.R + 4 + 3 * ((size_t)p.d * p.R + 4) + 16 + 2 * VJF_NWARP + 8 + (size_t)p.R * (p.R | 1) + 64;
   if (p.R > 128) return 0;
   if (p.rls64) b2 = std::max(b2, vjf_rls64_floats(p));

@@ -472,30 +472,10 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
     TK_STAMP(p, t, j, 0, 2);
     if (it > 0) tk_wait(&bars[BK_DW], (it - 1) & 1);
     TK_STAMP(p, t, j, 0, 3);
-    // phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) as a (hi, lo) pair of K-major SW128 images; pad columns and
-    // pad rows are zero
-    unsigned char* ph = pg;
-    unsigned char* plo = pg + pl.PWC * TBR * 128;
-    #pragma unroll 1
-    for (int i = ctid; i < TBR * pl.PW; i += TK_NCT) {
-      const int b = i / pl.PW, r = i - b * pl.PW;
-      float v = 0.f;
-      if (b < nb && r < R) {
-        float d2 = 0.f;
-        #pragma unroll 1
-        for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[r * du + c]; d2 = fmaf(df, df, d2); }
-        v = __expf(d2 * iw_s[r]);
-      }
-      const int o = sw128_off(b, r, TBR);
-      *reinterpret_cast<float*>(ph + o) = v;
-      *reinterpret_cast<float*>(plo + o) = v - tf32_trunc_f(v);
-    }
-    tk_signal(&bars[BK_CPHI]);
-    TK_STAMP(p, t, j, 0, 4);
     // observations of this tile (TMA) -> [u | m_s | l_s | 1] appended behind them (vjf/recognition.py:32-37; the ones column
     // carries the bias through the MMAs) and the lo image of the whole input tile, in one pass over the 16-byte pieces
     tk_wait(&bars[BK_YFULL0 + buf], (it / pl.NBUF) & 1);
-    TK_STAMP(p, t, j, 0, 5);
+    TK_STAMP(p, t, j, 0, 4);
     {
       float4* img = reinterpret_cast<float4*>(in_b);
       float4* dst = reinterpret_cast<float4*>(inlo_b);
@@ -526,6 +506,28 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
       }
     }
     tk_signal(&bars[BK_CX]);
+    TK_STAMP(p, t, j, 0, 5);
+    // (the features are computed while the forward MMAs of this tile run: the quadratic form needs them only after the RLS
+    // outputs of the previous step have arrived)
+    // phi = exp(-0.5 |xu - c|^2 / w^2) (vjf/functional.py:11-22) as a (hi, lo) pair of K-major SW128 images; pad columns and
+    // pad rows are zero
+    unsigned char* ph = pg;
+    unsigned char* plo = pg + pl.PWC * TBR * 128;
+    #pragma unroll 1
+    for (int i = ctid; i < TBR * pl.PW; i += TK_NCT) {
+      const int b = i / pl.PW, r = i - b * pl.PW;
+      float v = 0.f;
+      if (b < nb && r < R) {
+        float d2 = 0.f;
+        #pragma unroll 1
+        for (int c = 0; c < du; ++c) { const float df = xu_s[b * du + c] - c_s[r * du + c]; d2 = fmaf(df, df, d2); }
+        v = __expf(d2 * iw_s[r]);
+      }
+      const int o = sw128_off(b, r, TBR);
+      *reinterpret_cast<float*>(ph + o) = v;
+      *reinterpret_cast<float*>(plo + o) = v - tf32_trunc_f(v);
+    }
+    tk_signal(&bars[BK_CPHI]);
     TK_STAMP(p, t, j, 0, 6);
   }
 
@@ -746,7 +748,7 @@ static __device__ void tk_compute_tile(const StepParams& p, unsigned char* sb, u
 
 // Flush of everything a CTA accumulated over its tiles of one time step into its slot (all 16 warps).
 template <int DX>
-static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uint32_t tmem, TkAcc<DX>& acc, bool have_tiles) {
+static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uint32_t tmem, TkAcc<DX>& acc, bool have_tiles, int t = 0) {
   const TilePlan& pl = p.tp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, d = p.d, R = p.R, H = p.H[0];
@@ -759,8 +761,55 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
     return;
   }
   tc_fence_after();
-  // ---- tensor-memory accumulators: A = phi^T phi, b = phi^T dx ; dW1 (+ bias row) ----
-  {
+  // ---- tensor-memory accumulators: A = phi^T phi, b = phi^T dx ; dW1 (+ bias row).  A thread reads a ROW of an accumulator
+  //      (tensor-memory lane = row), so storing from the registers would touch 32 different lines per instruction; the blocks go
+  //      through a shared-memory stage instead and leave as whole 128-byte lines ----
+  if (pl.flush_stage) {
+    const int g = warp & 3, si = warp >> 2, row = g * 32 + lane;
+    float* stg = scr + pl.flush_floats;            // [128][LD]
+    const int LDg = pl.NQ + 4, LDw = H + 4;
+    // Gram block
+    #pragma unroll 1
+    for (int un = si; un < (pl.NQ >> 4); un += 4) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_gram + 16 * un, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(stg + row * LDg + 16 * un + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncthreads();
+    #pragma unroll 1
+    for (int i = tid; i < R * R; i += VJF_NT) { const int r = i / R, c = i - r * R; slot[p.pa + i] = stg[r * LDg + c]; }
+    #pragma unroll 1
+    for (int i = tid; i < R * d; i += VJF_NT) { const int r = i / d, k = i - r * d; slot[p.pb + i] = stg[r * LDg + pl.Rk + k]; }
+    #pragma unroll 1
+    for (int mb = 0; mb < pl.NBLK; ++mb) {
+      __syncthreads();
+      #pragma unroll 1
+      for (int un = si; un < (H >> 4); un += 4) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dw + mb * H + 16 * un, v);
+        if (mb >= (pl.CL0 >> 2)) {  // + the lo part of the input image (same rows of its own accumulator block)
+          float vl[16];
+          tmem_ld16(tmem + ((uint32_t)(g * 32) << 16) + pl.c_dwlo + (mb - (pl.CL0 >> 2)) * H + 16 * un, vl);
+          if (128 * mb + row >= 32 * pl.CL0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] += vl[q];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(stg + row * LDw + 16 * un + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      __syncthreads();
+      const int nvalid = min(128, p.K1 - 128 * mb);  // weight rows of this block (the bias row K1 follows them when it is in the block)
+      const int h4 = H >> 2;
+      float4* dst = reinterpret_cast<float4*>(slot + p.lay.mlp_w[0] + (size_t)(128 * mb) * H);
+      #pragma unroll 1
+      for (int i = tid; i < nvalid * h4; i += VJF_NT) { const int r = i / h4, c4 = i - r * h4; dst[i] = *reinterpret_cast<const float4*>(stg + r * LDw + 4 * c4); }
+      const int rb = p.K1 - 128 * mb;
+      if (rb >= 0 && rb < 128 && tid < H) slot[p.lay.mlp_b[0] + tid] = stg[rb * LDw + tid];
+    }
+  }
+  else {  // (the staging block does not fit the scratch of this plan: rows straight from the registers)
     const int g = warp & 3, si = warp >> 2, row = g * 32 + lane;
     #pragma unroll 1
     for (int un = si; un < (pl.NQ >> 4); un += 4) {
@@ -799,6 +848,7 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
     }
   }
   tc_fence_before();
+  TK_STAMP(p, t, 0, 0, 54);
   // ---- register accumulators through shared-memory scratch, summed in a fixed order ----
   // decoder: [task warp][(d + 1)][32]
   if (warp < pl.NCY * pl.RS) {
@@ -826,6 +876,7 @@ static __device__ void tk_flush_step(const StepParams& p, unsigned char* sb, uin
   }
   if (tid < d) scrs[16 * VJF_NSCAL + tid] = acc.ghvb;
   __syncthreads();
+  TK_STAMP(p, t, 0, 0, 55);
   #pragma unroll 1
   for (int i = tid; i < (d + 1) * D; i += VJF_NT) {
     const int k = i / D, j = i - k * D, cy = j >> 5, l = j & 31;
